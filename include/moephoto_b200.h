@@ -1,0 +1,142 @@
+/* moephoto_b200 — C ABI of the Blackwell (sm_100a) tiled SR / denoise engine.
+ *
+ * This is the drop-in boundary for MoePhoto's L3->L2 seam.  The reference has no
+ * FFI on this path (it is PyTorch eager); the entry points below are what a binding for the path
+ * replaces, one for one:
+ *
+ *   moe_model_load      <- imageProcess.initModel / getStateDict / castModel   imageProcess.py:304-334
+ *                          (+ the nn.Module constructors Net2x/Net3x/Net4x/NetDN  models.py:125-164)
+ *   moe_plan_workspace_bytes / moe_run_plan
+ *                       <- imageProcess.doCrop  (per-tile net call + blend + canvas store)
+ *                                                                          imageProcess.py:157-172
+ *                          with the per-tile network  MyNet.forward        models.py:117-123
+ *                          the seam blend             blend                 imageProcess.py:120-131
+ *                          and padImage / unpad       getPad                imageProcess.py:48-56,100-108
+ *   moe_axpby_f16       <- strengthOp                                       imageProcess.py:562
+ *   moe_to_planar_f16   <- toTorch (uint8 /255, wider /2^bits)              imageProcess.py:259-263
+ *   moe_to_output       <- toFloat + toOutput (x2^bits, clamp, truncate)    imageProcess.py:238-257
+ *   moe_enhance_host    <- the whole file->SR->output step chain of procedure.genProcess
+ *                          (procedure.py:156-201) for one image held in HOST memory.
+ *
+ * The tile list itself (prepare / getAnchors, imageProcess.py:19-35,73-118) is integer host logic and
+ * stays on the host: the caller passes it in as a MoePlan.
+ *
+ * Conventions: plain pointers and sizes only; every function returns MOE_OK (0) or a negative
+ * MoeStatus and never aborts the process; moe_last_error() gives the message for the calling thread's
+ * last failure.  All device pointers are on the engine's device.  `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream); work is enqueued on it and the call does not synchronise.
+ * There is NO CPU fallback: without a usable sm_100 device every compute entry point fails with
+ * MOE_ERR_NO_DEVICE.
+ */
+#ifndef MOEPHOTO_B200_H
+#define MOEPHOTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOE_ABI_VERSION 1
+
+typedef enum {
+  MOE_OK = 0,
+  MOE_ERR_INVALID = -1,      /* bad argument / malformed blob or plan            -> ValueError     */
+  MOE_ERR_NO_DEVICE = -2,    /* no CUDA device, or not compute capability 10.x   -> RuntimeError   */
+  MOE_ERR_NOMEM = -3,        /* workspace too small / allocation failed          -> MemoryError    */
+  MOE_ERR_CUDA = -4          /* a CUDA call or kernel launch failed              -> RuntimeError   */
+} MoeStatus;
+
+/* network families on the hot path (runSR.py:11-16, runDN.py:16-18) */
+typedef enum {
+  MOE_ARCH_NET2X = 2,        /* models.Net2x : a2 / p2 */
+  MOE_ARCH_NET3X = 3,        /* models.Net3x : a3 / p3 */
+  MOE_ARCH_NET4X = 4,        /* models.Net4x : a4 / p4 */
+  MOE_ARCH_NETDN = 1         /* models.NetDN : dn_lite5/10/15 */
+} MoeArch;
+
+typedef struct MoeEngine MoeEngine;
+typedef struct MoeModel MoeModel;
+
+/* One element of prepare()'s iterClip() (imageProcess.py:111-117), LR units unless noted. */
+typedef struct {
+  int32_t top, bottom, left, right;  /* tile rectangle in the (right/bottom padded) input image   */
+  int32_t top_t, left_t;             /* blend anchors: 0 = first tile, >0 = seam ends here,
+                                        <0 = seam ends |v| px before the tile's end (output px)     */
+  int32_t bsc, rsc;                  /* bottom / right edge of the tile on the canvas (output px)   */
+} MoeTile;
+
+typedef struct {
+  int32_t n_tiles;
+  int32_t scale;                     /* 1 (DN), 2, 3, 4                                              */
+  int32_t pad_sc;                    /* seam width in output px = padding * scale                    */
+  int32_t in_h, in_w;                /* input image size (before padImage)                           */
+  int32_t pad_h, pad_w;              /* rows / cols appended by padImage (reflect, then zeros)       */
+  int32_t out_h, out_w;              /* canvas size = in_h*scale, in_w*scale                         */
+  const MoeTile* tiles;              /* n_tiles entries, processed in this order                     */
+  const float* ramp;                 /* pad_sc blend weights sigma(9(i/pad_sc - 1/2)) (:109), already
+                                        rounded to the canvas dtype (fp16)                            */
+} MoePlan;
+
+/* ---- engine ------------------------------------------------------------------------------- */
+int moe_abi_version(void);
+const char* moe_last_error(void);
+int moe_engine_create(int device_id, MoeEngine** out);
+void moe_engine_destroy(MoeEngine* e);
+/* number of this library's kernels launched since the engine was created (bench.py "gpu_launches") */
+int64_t moe_engine_launch_count(const MoeEngine* e);
+/* 0 = tcgen05 tensor-core convolutions (default), 1 = plain SIMT convolutions (debug cross-check) */
+int moe_engine_set_conv_path(MoeEngine* e, int simt);
+
+/* ---- model -------------------------------------------------------------------------------- */
+/* `blob` is HOST memory in the packed format produced by moephoto_b200/weights.py (layout documented
+ * in csrc/blob.h); it is copied to the device, the caller may free it afterwards. */
+int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeModel** out);
+void moe_model_free(MoeModel* m);
+int moe_model_scale(const MoeModel* m);
+
+/* ---- doCrop ------------------------------------------------------------------------------- */
+/* Only canvas rows [row_lo,row_hi) are produced (row_lo = 0, row_hi = out_h for the whole image):
+ * a rank that owns a row band computes each tile restricted to the band plus a 16-LR-px recompute
+ * halo, which is exact (receptive field radius 15.75 LR px). */
+size_t moe_plan_workspace_bytes(const MoeModel* m, int planes, const MoePlan* plan, int row_lo, int row_hi);
+/* in : planes x in_h x in_w fp16, element strides given (column stride 1)
+ * out: planes x out_h x out_w fp16 canvas, element strides given (column stride 1)                */
+int moe_run_plan(MoeModel* m,
+                 const void* in, int64_t in_plane_stride, int64_t in_row_stride, int planes,
+                 void* canvas, int64_t out_plane_stride, int64_t out_row_stride,
+                 const MoePlan* plan, int row_lo, int row_hi,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- one layer (unit-test / profiling hook) -------------------------------------------------- */
+/* 3x3 convolution, 64 -> 64*r*r channels, NHWC fp16 (the building block of ARSB, models.py:76-80, and of
+ * genUpsampleBlock, models.py:29-33).  in: (n,h,w,64); out: (n,h*r,w*r,64); w_img: r*r swizzled 73 728-byte
+ * images ON THE DEVICE (csrc/blob.h); bias: r*r*64 floats on the device or NULL.
+ * epi: 0 plain, 1 PReLU(param), 2 out = skip + param*conv (skip may alias out), 3 PReLU(conv+bias) */
+int moe_conv3x3_c64(MoeEngine* e, const void* in, void* out, const void* skip, const void* w_img, const float* bias,
+                    int n, int h, int w, int r, int epi, float param, void* stream);
+
+/* ---- elementwise neighbours of the path --------------------------------------------------- */
+/* y = s*y + (1-s)*x on fp16, each product and the sum rounded to fp16 (strengthOp) */
+int moe_axpby_f16(MoeEngine* e, void* y, const void* x, float s, size_t count, void* stream);
+/* src: h x w x c interleaved integers, bits<=8 -> uint8 (/255), else uint16 (/2^bits);
+ * dst: c x h x w fp16.  `swap_rb` reads BGR as RGB (BGR2RGBTorch, procedure.py:129-135). */
+int moe_to_planar_f16(MoeEngine* e, const void* src, int bits, int h, int w, int c, int swap_rb,
+                      void* dst, void* stream);
+/* src: c x h x w fp16 ; dst: h x w x c, bits<=8 -> uint8, <=16 -> uint16 (the reference's int16/int32
+ * detour ends in the same bytes once toBuffer casts, imageProcess.py:231-236) */
+int moe_to_output(MoeEngine* e, const void* src, int bits, int h, int w, int c, int swap_rb,
+                  void* dst, void* stream);
+
+/* ---- whole step chain on HOST buffers (file -> SR/DN -> output) --------------------------- */
+/* host_in : in_h x in_w x 3 integers (bits as above); host_out: out_h x out_w x 3.
+ * Copies in, converts, runs the plan, converts and copies out on `stream`, then synchronises it.
+ * Uses the engine's internal device buffers (grown on demand). */
+int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePlan* plan,
+                     void* host_out, int bits_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOEPHOTO_B200_H */

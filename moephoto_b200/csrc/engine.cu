@@ -1,0 +1,504 @@
+// C ABI of the engine (include/moephoto_b200.h): model loading, the per-tile network schedule, the
+// on-device doCrop, and the frame conversions.  Host-side C++ only orchestrates kernel launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/moephoto_b200.h"
+#include "blob.h"
+#include "conv_tc.cuh"
+#include "kernels_simt.cuh"
+
+using namespace moe;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define MOE_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) return fail(MOE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int kHaloLR = 16;   // receptive-field radius of the whole net is 15.75 LR px
+constexpr int kNumBufs = 5;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct MoeEngine {
+  int device = 0;
+  int sm_count = 0;
+  EncodeTiledFn encode = nullptr;
+  std::atomic<int64_t> launches{0};
+  int simt = 0;
+  int base_offset_mode = 0;
+  bool smem_attr_set = false;
+  // grown-on-demand device buffers of moe_enhance_host: raw in, planar in, canvas, raw out, workspace
+  void* buf[kNumBufs] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kNumBufs] = {0, 0, 0, 0, 0};
+};
+
+struct MoeModel {
+  MoeEngine* e = nullptr;
+  int arch = 0, feat = 64, n_up = 0, r = 0, scale = 1;
+  uint8_t* d_blob = nullptr;
+  const float* first_w = nullptr;
+  float scalars[32] = {0};
+  const uint8_t* trunk_img[13] = {nullptr};
+  const uint8_t* up_img[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* up_bias[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* head_w[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+struct Guard {   // make the engine's device current for the duration of a call
+  int prev = -1;
+  bool ok = true;
+  explicit Guard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_launch(MoeEngine* e, const char* what) {
+  cudaError_t err = cudaPeekAtLastError();
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    return fail(MOE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(err));
+  }
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  return MOE_OK;
+}
+
+int grid_for(int64_t threads, int block, int sm_count) {
+  int64_t blocks = (threads + block - 1) / block;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(blocks, static_cast<int64_t>(sm_count) * 16)));
+}
+
+// ---- one 3x3 convolution 64 -> 64*r*r ----------------------------------------------------------
+int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, const __half* skip,
+                const uint8_t* w_img, const float* bias, int N, int H, int W, int r, int epi, float param)
+{
+  ConvParams p{};
+  p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
+  p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param;
+  p.base_offset_mode = e->base_offset_mode;
+  if (e->simt) {
+    const int64_t threads = static_cast<int64_t>(N) * H * W * r * r * 8;
+    conv3x3_simt_kernel<<<grid_for(threads, 256, e->sm_count), 256, 0, st>>>(p);
+    return check_launch(e, "conv3x3_simt_kernel");
+  }
+  const int ncg = r * r;                                    // one 64-channel chunk per CTA
+  const int G = std::max(ncg, e->sm_count / ncg * ncg);    // CTAs; multiple of ncg so a CTA keeps its chunk
+  p.strips = (W + kStripW - 1) / kStripW;
+  const int64_t base_items = static_cast<int64_t>(N) * p.strips * ncg;
+  int nseg = static_cast<int>((4ll * G + base_items - 1) / base_items);
+  nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
+  p.seg_rows = (H + nseg - 1) / nseg;
+  p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+  const int64_t items = base_items * p.nseg;
+  if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
+  p.items = static_cast<int>(items);
+  const int grid = static_cast<int>(std::min<int64_t>(G, items));   // items is a multiple of ncg
+
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  const cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(W) * 128, static_cast<cuuint64_t>(W) * H * 128};
+  const cuuint32_t box[4] = {64, kRowPx, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = e->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d H=%d W=%d", (int)cr, N, H, W);
+  if (!e->smem_attr_set) {
+    MOE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<1>::kSmemBytes));
+    e->smem_attr_set = true;
+  }
+  conv3x3_tc_kernel<1><<<grid, kConvThreads, ConvCfg<1>::kSmemBytes, st>>>(tmap, p);
+  return check_launch(e, "conv3x3_tc_kernel");
+}
+
+// ---- geometry of one tile restricted to a canvas row window ------------------------------------
+struct TileGeom {
+  bool active;
+  int c0, c1;            // computed LR rows, tile-relative
+  int H, W;              // computed LR rectangle
+  int keep_y0, keep_y1, keep_x0, keep_x1, ramp_y0, ramp_x0, blend_y1, blend_x1;
+};
+
+TileGeom tile_geom(const MoePlan& pl, const MoeTile& t, int row_lo, int row_hi) {
+  TileGeom g{};
+  const int sc = pl.scale, psc = pl.pad_sc;
+  const int th = t.bottom - t.top;
+  const int oy = t.top * sc, ox = t.left * sc;
+  const int lh = t.bsc - oy, lw = t.rsc - ox;          // tile extent on the canvas after unpad
+  int lt_r = t.top_t < 0 ? lh + t.top_t : t.top_t;     // blend(): negative anchors count from the end
+  int lt_c = t.left_t < 0 ? lw + t.left_t : t.left_t;
+  const int start_r = lt_r < 1 ? 0 : lt_r - psc;
+  const int start_c = lt_c < 1 ? 0 : lt_c - psc;
+  if (lt_r < 1) lt_r = 0;
+  if (lt_c < 1) lt_c = 0;
+  g.ramp_y0 = oy + start_r; g.blend_y1 = oy + lt_r;
+  g.ramp_x0 = ox + start_c; g.blend_x1 = ox + lt_c;
+  if (lt_r == 0) g.blend_y1 = g.ramp_y0;
+  if (lt_c == 0) g.blend_x1 = g.ramp_x0;
+  g.keep_y0 = std::max(g.ramp_y0, row_lo); g.keep_y1 = std::min(t.bsc, row_hi);
+  g.keep_x0 = g.ramp_x0; g.keep_x1 = t.rsc;
+  g.active = g.keep_y0 < g.keep_y1 && g.keep_x0 < g.keep_x1;
+  if (!g.active) return g;
+  const int lo = (g.keep_y0 - oy) / sc;
+  const int hi = (g.keep_y1 - oy + sc - 1) / sc;
+  g.c0 = std::max(0, lo - kHaloLR);
+  g.c1 = std::min(th, hi + kHaloLR);
+  g.H = g.c1 - g.c0;
+  g.W = t.right - t.left;
+  return g;
+}
+
+size_t tile_units(const MoeModel* m) {
+  if (m->n_up == 0) return 3;
+  if (m->n_up == 1) return 3 + 2 * static_cast<size_t>(m->r) * m->r;
+  return 3 + 4 + 32;
+}
+
+int validate_plan(const MoeModel* m, const MoePlan* pl, int planes, int row_lo, int row_hi) {
+  if (!m || !pl || !pl->tiles || pl->n_tiles <= 0) return fail(MOE_ERR_INVALID, "null model or empty plan");
+  if (pl->scale != m->scale) return fail(MOE_ERR_INVALID, "plan scale %d does not match model scale %d", pl->scale, m->scale);
+  if (planes <= 0 || pl->in_h <= 0 || pl->in_w <= 0) return fail(MOE_ERR_INVALID, "bad image shape");
+  if (pl->out_h != pl->in_h * pl->scale || pl->out_w != pl->in_w * pl->scale) return fail(MOE_ERR_INVALID, "canvas size mismatch");
+  if (pl->pad_sc > 0 && !pl->ramp) return fail(MOE_ERR_INVALID, "plan has a seam but no ramp");
+  if (row_lo < 0 || row_hi > pl->out_h || row_lo >= row_hi) return fail(MOE_ERR_INVALID, "bad row window [%d,%d)", row_lo, row_hi);
+  for (int i = 0; i < pl->n_tiles; ++i) {
+    const MoeTile& t = pl->tiles[i];
+    if (t.top < 0 || t.left < 0 || t.bottom <= t.top || t.right <= t.left || t.bottom > pl->in_h + pl->pad_h ||
+        t.right > pl->in_w + pl->pad_w || t.bsc > pl->out_h || t.rsc > pl->out_w || t.bsc <= t.top * pl->scale ||
+        t.rsc <= t.left * pl->scale)
+      return fail(MOE_ERR_INVALID, "tile %d is outside the padded image", i);
+  }
+  return MOE_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int moe_abi_version(void) { return MOE_ABI_VERSION; }
+const char* moe_last_error(void) { return g_err.c_str(); }
+
+int moe_engine_create(int device_id, MoeEngine** out)
+{
+  if (!out) return fail(MOE_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return fail(MOE_ERR_NO_DEVICE, "no CUDA device visible (this engine has no CPU fallback)");
+  }
+  if (device_id < 0 || device_id >= count) return fail(MOE_ERR_INVALID, "device %d out of range (%d devices)", device_id, count);
+  cudaDeviceProp prop;
+  MOE_CUDA(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return fail(MOE_ERR_NO_DEVICE, "device %d is sm_%d%d; this build is sm_100a only", device_id, prop.major, prop.minor);
+  MoeEngine* e = new MoeEngine();
+  e->device = device_id;
+  e->sm_count = prop.multiProcessorCount;
+  Guard g(device_id);
+  if (!g.ok) { delete e; return fail(MOE_ERR_CUDA, "cudaSetDevice(%d) failed", device_id); }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    delete e;
+    return fail(MOE_ERR_CUDA, "driver has no cuTensorMapEncodeTiled");
+  }
+  e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  const char* env = getenv("MOE_B200_SIMT");
+  e->simt = env && env[0] == '1';
+  env = getenv("MOE_B200_BASE_OFFSET_MODE");
+  e->base_offset_mode = env && env[0] == '1';
+  *out = e;
+  return MOE_OK;
+}
+
+void moe_engine_destroy(MoeEngine* e)
+{
+  if (!e) return;
+  Guard g(e->device);
+  for (int i = 0; i < kNumBufs; ++i) if (e->buf[i]) cudaFree(e->buf[i]);
+  delete e;
+}
+
+int64_t moe_engine_launch_count(const MoeEngine* e) { return e ? e->launches.load() : 0; }
+
+int moe_engine_set_conv_path(MoeEngine* e, int simt)
+{
+  if (!e) return fail(MOE_ERR_INVALID, "engine is null");
+  e->simt = simt & 1;
+  e->base_offset_mode = (simt >> 1) & 1;   // bit 1: descriptor experiment (tests only)
+  return MOE_OK;
+}
+
+int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeModel** out)
+{
+  if (!e || !blob || !out) return fail(MOE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (nbytes < sizeof(BlobHeader)) return fail(MOE_ERR_INVALID, "blob too small");
+  BlobHeader h;
+  memcpy(&h, blob, sizeof h);
+  if (h.magic != kBlobMagic || h.version != kBlobVersion) return fail(MOE_ERR_INVALID, "not a moephoto_b200 weight blob");
+  if (static_cast<int>(h.arch) != arch) return fail(MOE_ERR_INVALID, "blob is arch %u, asked for %d", h.arch, arch);
+  if (h.n_up > 2 || (h.n_up && h.r != 2 && h.r != 3) || (h.n_up == 2 && h.r != 2)) return fail(MOE_ERR_INVALID, "unsupported upsample layout");
+  if (nbytes < sizeof h + h.n_sections * sizeof(BlobEntry)) return fail(MOE_ERR_INVALID, "truncated directory");
+  Guard g(e->device);
+  if (!g.ok) return fail(MOE_ERR_CUDA, "cudaSetDevice failed");
+  MoeModel* m = new MoeModel();
+  m->e = e; m->arch = arch; m->feat = h.feat; m->n_up = h.n_up; m->r = h.r;
+  m->scale = h.n_up == 0 ? 1 : (h.n_up == 1 ? static_cast<int>(h.r) : 4);
+  if (cudaMalloc(&m->d_blob, nbytes) != cudaSuccess) { delete m; cudaGetLastError(); return fail(MOE_ERR_NOMEM, "cudaMalloc(%zu) for weights failed", nbytes); }
+  if (cudaMemcpy(m->d_blob, blob, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_CUDA, "weight upload failed"); }
+  const uint8_t* hb = static_cast<const uint8_t*>(blob);
+  bool have_scalars = false;
+  int n_trunk = 0, n_head = 0, n_up_img = 0, n_up_bias = 0;
+  const size_t n_chunks = h.n_up ? static_cast<size_t>(h.r) * h.r : 0;
+  for (uint32_t i = 0; i < h.n_sections; ++i) {
+    BlobEntry en;
+    memcpy(&en, hb + sizeof h + i * sizeof en, sizeof en);
+    bool bad = en.offset % 256 || en.offset + en.nbytes > nbytes;
+    const uint8_t* dp = m->d_blob + en.offset;
+    switch (en.kind) {
+      case SEC_FIRST_W: bad |= en.nbytes != 9 * 64 * 4; m->first_w = reinterpret_cast<const float*>(dp); break;
+      case SEC_SCALARS: bad |= en.nbytes != sizeof m->scalars; if (!bad) { memcpy(m->scalars, hb + en.offset, sizeof m->scalars); have_scalars = true; } break;
+      case SEC_TRUNK_IMG: bad |= en.index >= 13 || en.nbytes != kChunkImgBytes; if (!bad) { m->trunk_img[en.index] = dp; ++n_trunk; } break;
+      case SEC_UP_IMG: bad |= en.index >= 4 || en.nbytes != n_chunks * kChunkImgBytes; if (!bad) { m->up_img[en.index] = dp; ++n_up_img; } break;
+      case SEC_UP_BIAS: bad |= en.index >= 4 || en.nbytes != n_chunks * 64 * 4; if (!bad) { m->up_bias[en.index] = reinterpret_cast<const float*>(dp); ++n_up_bias; } break;
+      case SEC_HEAD_W: bad |= en.index >= 2 || en.nbytes != 9 * 64 * 4; if (!bad) { m->head_w[en.index] = reinterpret_cast<const float*>(dp); ++n_head; } break;
+      default: bad = true;
+    }
+    if (bad) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "bad blob section %u (kind %u index %u)", i, en.kind, en.index); }
+  }
+  const int want_up = 2 * static_cast<int>(h.n_up);
+  bool complete = m->first_w && have_scalars && n_trunk == 13 && n_head == 2 && n_up_img == want_up && n_up_bias == want_up;
+  for (int b = 0; b < 2 && complete; ++b)
+    for (uint32_t s = 0; s < h.n_up; ++s) complete = m->up_img[2 * b + s] && m->up_bias[2 * b + s];
+  if (!complete) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "blob is missing sections"); }
+  *out = m;
+  return MOE_OK;
+}
+
+void moe_model_free(MoeModel* m)
+{
+  if (!m) return;
+  Guard g(m->e->device);
+  if (m->d_blob) cudaFree(m->d_blob);
+  delete m;
+}
+
+int moe_model_scale(const MoeModel* m) { return m ? m->scale : 0; }
+
+size_t moe_plan_workspace_bytes(const MoeModel* m, int planes, const MoePlan* plan, int row_lo, int row_hi)
+{
+  if (validate_plan(m, plan, planes, row_lo, row_hi) != MOE_OK) return 0;
+  size_t worst = 0;
+  for (int i = 0; i < plan->n_tiles; ++i) {
+    const TileGeom g = tile_geom(*plan, plan->tiles[i], row_lo, row_hi);
+    if (!g.active) continue;
+    const size_t unit = align_up(static_cast<size_t>(planes) * g.H * g.W * 128, 1024);
+    worst = std::max(worst, unit * tile_units(m));
+  }
+  return worst + 1024;
+}
+
+int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t in_row_stride, int planes,
+                 void* canvas, int64_t out_plane_stride, int64_t out_row_stride,
+                 const MoePlan* plan, int row_lo, int row_hi, void* workspace, size_t workspace_bytes, void* stream)
+{
+  int rc = validate_plan(m, plan, planes, row_lo, row_hi);
+  if (rc != MOE_OK) return rc;
+  if (!in || !canvas || !workspace) return fail(MOE_ERR_INVALID, "null buffer");
+  if (workspace_bytes < moe_plan_workspace_bytes(m, planes, plan, row_lo, row_hi))
+    return fail(MOE_ERR_NOMEM, "workspace of %zu bytes is too small (need %zu)", workspace_bytes,
+                moe_plan_workspace_bytes(m, planes, plan, row_lo, row_hi));
+  MoeEngine* e = m->e;
+  Guard guard(e->device);
+  if (!guard.ok) return fail(MOE_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  const int sc = plan->scale, N = planes;
+
+  for (int ti = 0; ti < plan->n_tiles; ++ti) {
+    const MoeTile& t = plan->tiles[ti];
+    const TileGeom g = tile_geom(*plan, t, row_lo, row_hi);
+    if (!g.active) continue;
+    const int H = g.H, W = g.W;
+    const size_t unit = align_up(static_cast<size_t>(N) * H * W * 128, 1024);
+    __half* bufA = reinterpret_cast<__half*>(ws);              // `out`  = PReLU(conv_input(x))
+    __half* bufT = reinterpret_cast<__half*>(ws + unit);       // trunk  t
+    __half* bufM = reinterpret_cast<__half*>(ws + 2 * unit);   // ARSB mid
+    uint8_t* up0 = ws + 3 * unit;
+
+    // conv_input + PReLU                                                       models.py:118
+    FirstParams fp{};
+    fp.img = static_cast<const __half*>(in); fp.plane_stride = in_plane_stride; fp.row_stride = in_row_stride;
+    fp.in_h = plan->in_h; fp.in_w = plan->in_w; fp.pad_h = plan->pad_h; fp.pad_w = plan->pad_w;
+    fp.top = t.top + g.c0; fp.left = t.left; fp.N = N; fp.H = H; fp.W = W;
+    fp.w = m->first_w; fp.slope = m->scalars[0]; fp.out = bufA;
+    conv_first_kernel<<<grid_for(static_cast<int64_t>(N) * H * W * 8, 256, e->sm_count), 256, 0, st>>>(fp);
+    if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
+
+    // conv_input2, then six ARSBs: t += scale * conv_2(PReLU(conv_1(t)))        models.py:119, 76-80
+    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
+    for (int b = 0; b < 6; ++b) {
+      const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
+      if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+      if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
+    }
+
+    // the two upsample stacks u(out) and convt_R1(t)                          models.py:29-33,125-154
+    const __half* head_in[2] = {bufA, bufT};
+    if (m->n_up == 1) {
+      const size_t usz = unit * m->r * m->r;
+      for (int b = 0; b < 2; ++b) {
+        __half* dst = reinterpret_cast<__half*>(up0 + b * usz);
+        if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, m->r,
+                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b])) != MOE_OK) return rc;
+        head_in[b] = dst;
+      }
+    } else if (m->n_up == 2) {
+      __half* s1 = reinterpret_cast<__half*>(up0);                 // 4 units, shared by both branches
+      for (int b = 0; b < 2; ++b) {
+        __half* s2 = reinterpret_cast<__half*>(up0 + 4 * unit + b * 16 * unit);
+        if ((rc = launch_conv(e, st, b ? bufT : bufA, s1, nullptr, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, 2,
+                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b])) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, s1, s2, nullptr, m->up_img[2 * b + 1], m->up_bias[2 * b + 1], N, 2 * H, 2 * W, 2,
+                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b + 1])) != MOE_OK) return rc;
+        head_in[b] = s2;
+      }
+    }
+
+    // Conv3x3(F,1) heads, branch sum, seam blend, canvas store          models.py:38; imageProcess.py:164-170
+    HeadParams hp{};
+    hp.u = head_in[0]; hp.r = head_in[1]; hp.wu = m->head_w[0]; hp.wr = m->head_w[1];
+    hp.N = N; hp.H = H * sc; hp.W = W * sc;
+    hp.oy = (t.top + g.c0) * sc; hp.ox = t.left * sc;
+    hp.keep_y0 = g.keep_y0; hp.keep_y1 = g.keep_y1; hp.keep_x0 = g.keep_x0; hp.keep_x1 = g.keep_x1;
+    hp.ramp_y0 = g.ramp_y0; hp.ramp_x0 = g.ramp_x0; hp.blend_y1 = g.blend_y1; hp.blend_x1 = g.blend_x1;
+    hp.ramp = plan->ramp; hp.canvas = static_cast<__half*>(canvas);
+    hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
+    dim3 hgrid((hp.W + 127) / 128, hp.H, N);
+    if (hgrid.y > 65535u || hgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the head kernel grid");
+    head_blend_kernel<<<hgrid, 128, 0, st>>>(hp);
+    if ((rc = check_launch(e, "head_blend_kernel")) != MOE_OK) return rc;
+  }
+  return MOE_OK;
+}
+
+int moe_conv3x3_c64(MoeEngine* e, const void* in, void* out, const void* skip, const void* w_img, const float* bias,
+                    int n, int h, int w, int r, int epi, float param, void* stream)
+{
+  if (!e || !in || !out || !w_img || n <= 0 || h <= 0 || w <= 0 || r < 1 || r > 3 || epi < 0 || epi > 3)
+    return fail(MOE_ERR_INVALID, "bad argument");
+  if ((epi == EPI_SCALE_SKIP && !skip) || (epi == EPI_BIAS_PRELU && !bias)) return fail(MOE_ERR_INVALID, "epilogue operand missing");
+  Guard g(e->device);
+  return launch_conv(e, static_cast<cudaStream_t>(stream), static_cast<const __half*>(in), static_cast<__half*>(out),
+                     static_cast<const __half*>(skip), static_cast<const uint8_t*>(w_img), bias, n, h, w, r, epi, param);
+}
+
+int moe_axpby_f16(MoeEngine* e, void* y, const void* x, float s, size_t count, void* stream)
+{
+  if (!e || !y || !x) return fail(MOE_ERR_INVALID, "null argument");
+  if (count == 0) return MOE_OK;
+  Guard g(e->device);
+  axpby_f16_kernel<<<grid_for(static_cast<int64_t>(count), 256, e->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__half*>(y), static_cast<const __half*>(x), s, 1.f - s, count);
+  return check_launch(e, "axpby_f16_kernel");
+}
+
+int moe_to_planar_f16(MoeEngine* e, const void* src, int bits, int h, int w, int c, int swap_rb, void* dst, void* stream)
+{
+  if (!e || !src || !dst || h <= 0 || w <= 0 || c <= 0 || bits < 1 || bits > 16) return fail(MOE_ERR_INVALID, "bad argument");
+  Guard g(e->device);
+  const int grid = grid_for(static_cast<int64_t>(h) * w, 256, e->sm_count);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bits <= 8)
+    to_planar_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), h, w, c, swap_rb, 0.f, 1, static_cast<__half*>(dst));
+  else
+    to_planar_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(src), h, w, c, swap_rb, 1.f / static_cast<float>(1 << bits), 0,
+                                                      static_cast<__half*>(dst));
+  return check_launch(e, "to_planar_kernel");
+}
+
+int moe_to_output(MoeEngine* e, const void* src, int bits, int h, int w, int c, int swap_rb, void* dst, void* stream)
+{
+  if (!e || !src || !dst || h <= 0 || w <= 0 || c <= 0 || bits < 1 || bits > 16) return fail(MOE_ERR_INVALID, "bad argument");
+  Guard g(e->device);
+  const int grid = grid_for(static_cast<int64_t>(h) * w, 256, e->sm_count);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float quant = static_cast<float>(1 << bits);
+  if (bits <= 8)
+    to_output_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const __half*>(src), h, w, c, swap_rb, quant, static_cast<uint8_t*>(dst));
+  else
+    to_output_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const __half*>(src), h, w, c, swap_rb, quant, static_cast<uint16_t*>(dst));
+  return check_launch(e, "to_output_kernel");
+}
+
+static int ensure_buf(MoeEngine* e, int i, size_t bytes)
+{
+  if (e->cap[i] >= bytes) return MOE_OK;
+  if (e->buf[i]) { cudaFree(e->buf[i]); e->buf[i] = nullptr; e->cap[i] = 0; }
+  if (cudaMalloc(&e->buf[i], bytes) != cudaSuccess) { cudaGetLastError(); return fail(MOE_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes); }
+  e->cap[i] = bytes;
+  return MOE_OK;
+}
+
+int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePlan* plan, void* host_out, int bits_out, void* stream)
+{
+  int rc = validate_plan(m, plan, 3, 0, plan ? plan->out_h : 0);
+  if (rc != MOE_OK) return rc;
+  if (!host_in || !host_out) return fail(MOE_ERR_INVALID, "null host buffer");
+  MoeEngine* e = m->e;
+  Guard guard(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t ipx = static_cast<size_t>(plan->in_h) * plan->in_w, opx = static_cast<size_t>(plan->out_h) * plan->out_w;
+  const size_t in_raw = ipx * 3 * (bits_in <= 8 ? 1 : 2), out_raw = opx * 3 * (bits_out <= 8 ? 1 : 2);
+  const size_t wsb = moe_plan_workspace_bytes(m, 3, plan, 0, plan->out_h);
+  if ((rc = ensure_buf(e, 0, in_raw)) || (rc = ensure_buf(e, 1, ipx * 3 * 2)) || (rc = ensure_buf(e, 2, opx * 3 * 2)) ||
+      (rc = ensure_buf(e, 3, out_raw)) || (rc = ensure_buf(e, 4, wsb)))
+    return rc;
+  MOE_CUDA(cudaMemcpyAsync(e->buf[0], host_in, in_raw, cudaMemcpyHostToDevice, st));
+  if ((rc = moe_to_planar_f16(e, e->buf[0], bits_in, plan->in_h, plan->in_w, 3, 0, e->buf[1], st)) != MOE_OK) return rc;
+  if ((rc = moe_run_plan(m, e->buf[1], static_cast<int64_t>(ipx), plan->in_w, 3, e->buf[2], static_cast<int64_t>(opx), plan->out_w,
+                         plan, 0, plan->out_h, e->buf[4], e->cap[4], st)) != MOE_OK) return rc;
+  if ((rc = moe_to_output(e, e->buf[2], bits_out, plan->out_h, plan->out_w, 3, 0, e->buf[3], st)) != MOE_OK) return rc;
+  MOE_CUDA(cudaMemcpyAsync(host_out, e->buf[3], out_raw, cudaMemcpyDeviceToHost, st));
+  MOE_CUDA(cudaStreamSynchronize(st));
+  return MOE_OK;
+}
+
+}  // extern "C"

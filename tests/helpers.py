@@ -1,0 +1,100 @@
+"""Shared helpers of the test-suite: golden fixtures (tests/golden, generated from the unmodified
+reference by make_golden.py), the oracle runners, and the engine runners that go through the
+reference-shaped API (runSR.getOpt / runSR.sr / runDN.getOpt / imageProcess.RGBFilter)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+_cases = None
+WEIGHT_OF = {('sr', 2): 'a2', ('sr', 3): 'a3', ('sr', 4): 'a4', ('dn', 'lite15'): 'dn_lite15', ('dn', 'lite5'): 'dn_lite5'}
+
+
+def _load():
+  global _cases
+  if _cases is None:
+    z = np.load(os.path.join(GOLD, 'cases.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    _cases = (z, meta)
+  return _cases
+
+
+def case_names():
+  return list(_load()[1].keys())
+
+
+def load_case(name):
+  z, meta = _load()
+  c = dict(meta[name])
+  c['name'] = name
+  c['img'] = z[name + '.img']
+  c['ref'] = z[name + '.ref']
+  c['alpha'] = z[name + '.alpha'] if (name + '.alpha') in z.files else None
+  c['weights'] = WEIGHT_OF[(c['kind'], c['arg'])]
+  return c
+
+
+def load_weights(key):
+  """fp16 copy of a reference checkpoint (tests/golden/weights_<key>.npz) as a float32 numpy state dict"""
+  return {k: v.astype(np.float32) for k, v in np.load(os.path.join(GOLD, 'weights_%s.npz' % key)).items()}
+
+
+def case_input(c, dtype=np.float32):
+  from oracle import tiling as T
+  x = T.to_planar(c['img'], 8, dtype)
+  if c['alpha'] is not None:
+    x = np.concatenate([x, c['alpha'][None].astype(dtype)], 0)
+  return x
+
+
+def oracle_plan(c, planes=3):
+  from oracle import tiling as T
+  h, w = c['img'].shape[:2]
+  return T.make_plan((planes, h, w), c['ram'], c['ram_coef'], c['pad'], c['scale'], 8, c['crop'])
+
+
+def run_case_oracle(c, mode='fp32', backend='c'):
+  from oracle import net as N, tiling as T
+  sd = load_weights(c['weights'])
+  dt = np.float32 if mode == 'fp32' else np.float16
+  x = case_input(c, dt).astype(np.float32)
+  plan = oracle_plan(c)
+  net = lambda a: N.forward(sd, a, mode=mode, backend=backend)
+  if c['kind'] == 'sr':
+    return T.do_crop(net, x, plan, dt).astype(np.float32)
+  return T.rgb_filter(net, x, plan, 1.0, dt).astype(np.float32)
+
+
+def run_case_engine(c):
+  """through the reference-shaped API, on the GPU"""
+  import torch
+  from moephoto_b200 import runSR, runDN, imageProcess as IP
+  from moephoto_b200.config import config
+  sd = load_weights(c['weights'])
+  config.freeMemOverride = c['ram']
+  x = IP.toTorch(8)(c['img'])
+  if c['alpha'] is not None:
+    x = torch.cat([x, torch.from_numpy(c['alpha'])[None].to(x.device, x.dtype)], 0)
+  try:
+    if c['kind'] == 'sr':
+      config.crop_sr = c['crop'] if c['crop'] else 'auto'
+      opt = runSR.getOpt({'model': 'a', 'scale': c['arg']}, weights=sd)
+      y = runSR.sr(opt)(x)
+    else:
+      config.crop_dn = c['crop'] if c['crop'] else 'auto'
+      opt = runDN.getOpt({'model': c['arg']}, weights=sd)
+      y = IP.RGBFilter(opt)(x)
+    assert [list(t) for t in opt.plan.tiles] == c['tiles'], 'engine tile plan differs from the reference plan'
+    return y.float().cpu().numpy()
+  finally:
+    config.freeMemOverride = None
+    config.crop_sr = config.crop_dn = 'auto'
+
+
+def psnr(a, b):
+  return 10 * np.log10(1.0 / max(float(np.mean((a.astype(np.float64) - b) ** 2)), 1e-20))
