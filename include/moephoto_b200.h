@@ -86,6 +86,12 @@ int moe_engine_create(int device_id, MoeEngine** out);
 void moe_engine_destroy(MoeEngine* e);
 /* number of this library's kernels launched since the engine was created (bench.py "gpu_launches") */
 int64_t moe_engine_launch_count(const MoeEngine* e);
+/* Per-launch device timing for roofline reports: while enabled, every kernel launch is bracketed by
+ * a CUDA event pair on its stream.  _read waits for them, returns per class (0 conv_input, 1 conv3x3,
+ * 2 heads+blend, 3 unused) the summed milliseconds, the summed algorithmic work (FLOPs for class 1,
+ * bytes otherwise) and the launch count, and resets the counters. */
+int moe_engine_profile(MoeEngine* e, int enable);
+int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t launches[4]);
 /* 0 = tcgen05 tensor-core convolutions (default), 1 = plain SIMT convolutions (debug cross-check) */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
 

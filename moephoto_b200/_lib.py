@@ -39,6 +39,8 @@ SYMBOLS = {
   'moe_engine_create': (_i, [_i, _pp]),
   'moe_engine_destroy': (None, [_vp]),
   'moe_engine_launch_count': (_i64, [_vp]),
+  'moe_engine_profile': (_i, [_vp, _i]),
+  'moe_engine_profile_read': (_i, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
   'moe_engine_set_conv_path': (_i, [_vp, _i]),
   'moe_model_load': (_i, [_vp, _i, _vp, _sz, _pp]),
   'moe_model_free': (None, [_vp]),

@@ -7,6 +7,9 @@
 //                into a ring of row slots; the nine taps are nine *views* of those three slots: the
 //                smem descriptor's start address is moved by dx*128 B (next pixel) and k*32 B (next
 //                16 channels) — no im2col copy, no re-read of a row for its three vertical uses.
+//                (Measured on B200, profiles/r01_diag_first_contact.log: the 128B swizzle is a function
+//                of the absolute smem address, so a start address that is not 1024-aligned needs NO
+//                base_offset in the descriptor; setting base_offset = (addr>>7)&7 gives garbage.)
 //   * B operand= the layer's weights for NCH 64-channel output chunks, resident in smem for the whole
 //                kernel (pre-swizzled on the host, fetched with cp.async.bulk).
 //   * zero padding at the tile border is TMA out-of-bounds fill (x = -1, x = W, y = -1, y = H).
@@ -35,7 +38,6 @@ struct ConvParams {
   int epi;
   float param;            // PReLU slope or residual scale
   int strips, nseg, seg_rows, items;
-  int base_offset_mode;   // descriptor experiment switch, 0 in production
 };
 
 constexpr int kStripW = 128;
@@ -157,10 +159,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams p
             for (int dx = 0; dx < 3; ++dx) {
               const uint32_t a0 = abase + dx * 128;
               const uint32_t b0 = wsm + (dy * 3 + dx) * (NCH * 8192);
-              const uint32_t boff = p.base_offset_mode ? ((a0 >> 7) & 7) : 0;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a0 + k * 32, 1024, boff),
+                ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a0 + k * 32, 1024, 0),
                                 ptx::smem_desc_sw128(b0 + k * 32, 1024, 0), idesc, (dy | dx | k) != 0);
               }
             }
@@ -173,6 +174,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams p
         ptx::mma_commit(empty + 8 * ((cons + nrows + 1) % S));
         cons += nrows + 2;
       }
+      // drain: commits complete in order, so once this one lands no arrive is still in flight
+      ptx::mma_commit(wbar);
+      ptx::mbar_wait(wbar, 1);
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)

@@ -57,8 +57,14 @@ struct MoeEngine {
   EncodeTiledFn encode = nullptr;
   std::atomic<int64_t> launches{0};
   int simt = 0;
-  int base_offset_mode = 0;
+  int cur_feat = 64;       // real filter count of the model being run (48 for NetDN) — FLOP accounting only
   bool smem_attr_set = false;
+  // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3, 2 heads, 3 frame I/O
+  bool profiling = false;
+  struct Span { int cls; cudaEvent_t a, b; double work; };
+  std::vector<Span> spans;
+  double prof_ms[4] = {0, 0, 0, 0}, prof_work[4] = {0, 0, 0, 0};
+  int64_t prof_n[4] = {0, 0, 0, 0};
   // grown-on-demand device buffers of moe_enhance_host: raw in, planar in, canvas, raw out, workspace
   void* buf[kNumBufs] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t cap[kNumBufs] = {0, 0, 0, 0, 0};
@@ -88,6 +94,20 @@ struct Guard {   // make the engine's device current for the duration of a call
   ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// RAII bracket: records an event pair around one kernel launch when profiling is on
+struct Timed {
+  MoeEngine* e; cudaStream_t st; int idx = -1;
+  Timed(MoeEngine* e_, cudaStream_t st_, int cls, double work) : e(e_), st(st_) {
+    if (!e->profiling) return;
+    MoeEngine::Span s{cls, nullptr, nullptr, work};
+    if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+    cudaEventRecord(s.a, st);
+    e->spans.push_back(s);
+    idx = static_cast<int>(e->spans.size()) - 1;
+  }
+  ~Timed() { if (idx >= 0) cudaEventRecord(e->spans[idx].b, st); }
+};
+
 int check_launch(MoeEngine* e, const char* what) {
   cudaError_t err = cudaPeekAtLastError();
   if (err != cudaSuccess) {
@@ -110,7 +130,8 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   ConvParams p{};
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
   p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param;
-  p.base_offset_mode = e->base_offset_mode;
+  // algorithmic FLOPs: 2 * 9 taps * Cin * Cout per input pixel (padded channels are not counted)
+  Timed timed(e, st, 1, 2.0 * 9 * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
   if (e->simt) {
     const int64_t threads = static_cast<int64_t>(N) * H * W * r * r * 8;
     conv3x3_simt_kernel<<<grid_for(threads, 256, e->sm_count), 256, 0, st>>>(p);
@@ -195,6 +216,7 @@ int validate_plan(const MoeModel* m, const MoePlan* pl, int planes, int row_lo, 
   if (planes <= 0 || pl->in_h <= 0 || pl->in_w <= 0) return fail(MOE_ERR_INVALID, "bad image shape");
   if (pl->out_h != pl->in_h * pl->scale || pl->out_w != pl->in_w * pl->scale) return fail(MOE_ERR_INVALID, "canvas size mismatch");
   if (pl->pad_sc > 0 && !pl->ramp) return fail(MOE_ERR_INVALID, "plan has a seam but no ramp");
+  if (pl->pad_sc < 0 || pl->pad_sc > kMaxSeam) return fail(MOE_ERR_INVALID, "seam of %d px is wider than %d", pl->pad_sc, kMaxSeam);
   if (row_lo < 0 || row_hi > pl->out_h || row_lo >= row_hi) return fail(MOE_ERR_INVALID, "bad row window [%d,%d)", row_lo, row_hi);
   for (int i = 0; i < pl->n_tiles; ++i) {
     const MoeTile& t = pl->tiles[i];
@@ -241,8 +263,6 @@ int moe_engine_create(int device_id, MoeEngine** out)
   e->encode = reinterpret_cast<EncodeTiledFn>(fn);
   const char* env = getenv("MOE_B200_SIMT");
   e->simt = env && env[0] == '1';
-  env = getenv("MOE_B200_BASE_OFFSET_MODE");
-  e->base_offset_mode = env && env[0] == '1';
   *out = e;
   return MOE_OK;
 }
@@ -257,11 +277,36 @@ void moe_engine_destroy(MoeEngine* e)
 
 int64_t moe_engine_launch_count(const MoeEngine* e) { return e ? e->launches.load() : 0; }
 
+int moe_engine_profile(MoeEngine* e, int enable)
+{
+  if (!e) return fail(MOE_ERR_INVALID, "engine is null");
+  e->profiling = enable != 0;
+  return MOE_OK;
+}
+
+int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t launches[4])
+{
+  if (!e || !ms || !work || !launches) return fail(MOE_ERR_INVALID, "null argument");
+  Guard g(e->device);
+  for (auto& s : e->spans) {
+    float t = 0.f;
+    if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
+      e->prof_ms[s.cls] += t; e->prof_work[s.cls] += s.work; e->prof_n[s.cls] += 1;
+    }
+    cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+  }
+  e->spans.clear();
+  for (int i = 0; i < 4; ++i) {
+    ms[i] = e->prof_ms[i]; work[i] = e->prof_work[i]; launches[i] = e->prof_n[i];
+    e->prof_ms[i] = e->prof_work[i] = 0; e->prof_n[i] = 0;
+  }
+  return MOE_OK;
+}
+
 int moe_engine_set_conv_path(MoeEngine* e, int simt)
 {
   if (!e) return fail(MOE_ERR_INVALID, "engine is null");
   e->simt = simt & 1;
-  e->base_offset_mode = (simt >> 1) & 1;   // bit 1: descriptor experiment (tests only)
   return MOE_OK;
 }
 
@@ -369,7 +414,11 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     fp.in_h = plan->in_h; fp.in_w = plan->in_w; fp.pad_h = plan->pad_h; fp.pad_w = plan->pad_w;
     fp.top = t.top + g.c0; fp.left = t.left; fp.N = N; fp.H = H; fp.W = W;
     fp.w = m->first_w; fp.slope = m->scalars[0]; fp.out = bufA;
+    e->cur_feat = m->feat;
+    {
+    Timed timed(e, st, 0, static_cast<double>(N) * H * W * (2 + 128));     // bytes: read 1 fp16, write 64 fp16
     conv_first_kernel<<<grid_for(static_cast<int64_t>(N) * H * W * 8, 256, e->sm_count), 256, 0, st>>>(fp);
+    }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 
     // conv_input2, then six ARSBs: t += scale * conv_2(PReLU(conv_1(t)))        models.py:119, 76-80
@@ -409,11 +458,15 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     hp.oy = (t.top + g.c0) * sc; hp.ox = t.left * sc;
     hp.keep_y0 = g.keep_y0; hp.keep_y1 = g.keep_y1; hp.keep_x0 = g.keep_x0; hp.keep_x1 = g.keep_x1;
     hp.ramp_y0 = g.ramp_y0; hp.ramp_x0 = g.ramp_x0; hp.blend_y1 = g.blend_y1; hp.blend_x1 = g.blend_x1;
-    hp.ramp = plan->ramp; hp.canvas = static_cast<__half*>(canvas);
+    for (int i = 0; i < plan->pad_sc; ++i) hp.ramp[i] = plan->ramp[i];
+    hp.canvas = static_cast<__half*>(canvas);
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
     dim3 hgrid((hp.W + 127) / 128, hp.H, N);
     if (hgrid.y > 65535u || hgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the head kernel grid");
+    {
+    Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (2 * 128 + 2));   // bytes: two 64-ch fp16 reads, one fp16 write
     head_blend_kernel<<<hgrid, 128, 0, st>>>(hp);
+    }
     if ((rc = check_launch(e, "head_blend_kernel")) != MOE_OK) return rc;
   }
   return MOE_OK;

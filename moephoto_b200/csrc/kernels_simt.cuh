@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p)
   }
 }
 
+constexpr int kMaxSeam = 64;
+
 struct HeadParams {
   const __half* u;                 // NHWC (N,H,W,64): input of Conv3x3(F,1) in branch `u`
   const __half* r;                 // same for branch `convt_R1`
@@ -85,7 +87,7 @@ struct HeadParams {
   int keep_y0, keep_y1, keep_x0, keep_x1;   // rows/cols [y0,y1) x [x0,x1) are written
   int ramp_y0, ramp_x0;            // first row / col of the seam (unclipped start of the kept region)
   int blend_y1, blend_x1;          // rows [ramp_y0, blend_y1) / cols [ramp_x0, blend_x1) are blended with the canvas
-  const float* ramp;               // pad_sc weights
+  float ramp[kMaxSeam];            // pad_sc weights, by value (the plan's ramp lives in host memory)
   __half* canvas;                  // planes x out_h x out_w (strided)
   int64_t plane_stride, row_stride;
 };

@@ -51,8 +51,17 @@ class Engine:
   def launches(self):
     return int(self.lib.moe_engine_launch_count(self.handle))
 
-  def set_conv_path(self, simt=False, base_offset_mode=False):
-    _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(base_offset_mode)) << 1)))
+  def profile(self, enable):
+    _lib.check(self.lib.moe_engine_profile(self.handle, int(bool(enable))))
+
+  def profile_read(self):
+    """-> {class: (ms, work, launches)} for conv_input / conv3x3 / head, and resets the counters"""
+    ms, work, n = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_int64 * 4)()
+    _lib.check(self.lib.moe_engine_profile_read(self.handle, ms, work, n))
+    return {k: (ms[i], work[i], n[i]) for i, k in enumerate(('conv_input', 'conv3x3', 'head', 'other'))}
+
+  def set_conv_path(self, simt=False):
+    _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt))))
 
   def get_workspace(self, nbytes):
     if self.workspace is None or self.workspace.numel() < nbytes:

@@ -130,3 +130,28 @@ def forward(sd, x, mode='fp32', backend='c'):
 
   y = branch(out, 'u') + branch(t, 'convt_R1')                            # models.py:38,121-123
   return q(y)
+
+
+def forward_torch(sd, x):
+  """The same forward, fp32, entirely in PyTorch CPU functional ops (conv2d / pixel_shuffle / prelu) —
+  operation for operation what the reference's nn.Modules execute on its CPU path (oneDNN), without
+  numpy glue.  Used for the timed CPU baseline (bench.py) and cross-checked against forward() in
+  tests/test_oracle_golden.py.  x: (N,1,h,w) float32 ndarray or tensor -> ndarray."""
+  import torch
+  import torch.nn.functional as F
+  T = lambda k: torch.from_numpy(np.ascontiguousarray(sd[k], dtype=np.float32))
+  _, ups = ARCH[arch_of_state_dict(sd)]
+  with torch.no_grad():
+    x = torch.as_tensor(np.asarray(x, dtype=np.float32)) if not torch.is_tensor(x) else x
+    cv = lambda a, k, b=None: F.conv2d(a, T(k), None if b is None else T(b), padding=1)
+    out = F.prelu(cv(x, 'conv_input.weight'), T('relu.weight'))
+    t = cv(out, 'conv_input2.weight')
+    for i in range(1, 7):
+      p = 'convt_F%d.0.' % i
+      t = t + T(p + 'scale.scale') * cv(F.prelu(cv(t, p + 'conv_1.weight'), T(p + 'relu.weight')), p + 'conv_2.weight')
+
+    def branch(a, name):
+      for j, r in enumerate(ups):
+        a = F.prelu(F.pixel_shuffle(cv(a, '%s.%d.0.weight' % (name, j), '%s.%d.0.bias' % (name, j)), r), T('%s.%d.2.weight' % (name, j)))
+      return cv(a, ('%s.%d.weight' % (name, len(ups))) if ups else (name + '.weight'))
+    return (branch(out, 'u') + branch(t, 'convt_R1')).numpy()

@@ -147,11 +147,13 @@ def _blend_axis(r, x, lt, pad, axis, ramp, q):
   return np.concatenate([b, tail], axis), x[tuple(sl)]
 
 
-def do_crop(net, x, plan, dtype=np.float32):
+def do_crop(net, x, plan, dtype=np.float32, ramp=None):
   """imageProcess.py:157-172.  x: (C,H,W); net maps (C,1,h,w)->(C,1,s*h,s*w).  The canvas is `dtype`
   (float32 = reference CPU path; float16 = reference GPU path, every elementwise op rounds)."""
   q = (lambda a: a.astype(dtype)) if dtype != np.float32 else (lambda a: a)
-  ramp = blend_ramp(plan.pad_sc, dtype) if plan.pad_sc else np.zeros(0, dtype)
+  if ramp is None:   # (a caller may pass the reference's own ramp: libm sigmoids differ in the last ulp)
+    ramp = blend_ramp(plan.pad_sc, dtype) if plan.pad_sc else np.zeros(0, dtype)
+  ramp = np.asarray(ramp, dtype=dtype)
   sc, psc = plan.scale, plan.pad_sc
   xp = _pad_axis(_pad_axis(x, -1, plan.pad_w), -2, plan.pad_h)[:, None]
   canvas = np.zeros((x.shape[0], plan.out_h, plan.out_w), dtype=dtype)   # reference: new_empty

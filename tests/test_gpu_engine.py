@@ -1,0 +1,271 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the reference-shaped API and the C ABI,
+against the oracle and the golden vectors of the unmodified reference.
+
+Tolerances, all stated here:
+  * vs oracle mode 'f16io' (identical rounding points, fp32 accumulation in another order): max-abs <= 1e-3
+    (one fp16 ulp at 1.0 is 9.77e-4) — BASELINE's "1e-3 max-abs fp16".
+  * vs the reference's own fp32 CPU output (goldens): PSNR >= 60 dB (measured 71-75 dB), max-abs <= 1.5e-2
+    (the tail is the fp16 rounding of the WEIGHTS, which the reference's GPU path has too).
+  * integer frame conversions, band sharding, determinism: bit-exact.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_ref(x, w, bias, r, epi, param, skip):
+  xn = x.float().permute(0, 3, 1, 2)
+  y = torch.nn.functional.conv2d(xn, w.float(), None if bias is None else bias.float(), padding=1)
+  if epi == 1:
+    y = torch.where(y >= 0, y, param * y)
+  elif epi == 2:
+    y = skip.float().permute(0, 3, 1, 2) + param * y
+  elif epi == 3:
+    y = torch.nn.functional.pixel_shuffle(y, r) if r > 1 else y
+    y = torch.where(y >= 0, y, param * y)
+  return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _run_conv(eng, x, w, bias, r, epi, param, skip):
+  from moephoto_b200 import _lib, weights as W
+  n, h, wd, _ = x.shape
+  w16 = w.half().cpu().numpy()
+  imgs, bs = [], []
+  for i in range(r):
+    for j in range(r):
+      sel = np.arange(64) * r * r + i * r + j
+      imgs.append(W.conv_image(w16[sel]))
+      if bias is not None:
+        bs.append(bias.float().cpu().numpy()[sel])
+  img = torch.from_numpy(np.concatenate(imgs)).cuda()
+  bdev = torch.from_numpy(np.stack(bs).astype(np.float32)).cuda() if bias is not None else None
+  out = skip.clone() if epi == 2 else torch.full((n, h * r, wd * r, 64), float('nan'), dtype=torch.half, device='cuda')
+  _lib.check(eng.lib.moe_conv3x3_c64(eng.handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                     ctypes.c_void_p(out.data_ptr()) if epi == 2 else None, ctypes.c_void_p(img.data_ptr()),
+                                     ctypes.c_void_p(bdev.data_ptr()) if bdev is not None else None, n, h, wd, r, epi, float(param), None))
+  torch.cuda.synchronize()
+  return out
+
+
+CONV_CASES = [(1, 1, 1, 1, 0), (1, 8, 128, 1, 0), (1, 20, 129, 1, 1), (2, 33, 200, 1, 2), (3, 40, 48, 1, 1), (1, 17, 300, 2, 3),
+              (1, 12, 130, 3, 3), (3, 70, 257, 1, 0), (1, 3, 1000, 1, 2), (2, 300, 127, 1, 1), (1, 9, 7, 2, 3)]
+
+
+@pytest.mark.parametrize('n,h,w,r,epi', CONV_CASES)
+def test_conv3x3_tcgen05_matches_fp32_reference_and_simt(engine, n, h, w, r, epi):
+  """one layer: empty-ish, ragged (w not a multiple of the 128-px strip), every epilogue, PixelShuffle 2 and 3"""
+  g = torch.Generator().manual_seed(n * 7919 + h * 31 + w)
+  x = (torch.randn(n, h, w, 64, generator=g) * 0.5).half().cuda()
+  wt = (torch.randn(64 * r * r, 64, 3, 3, generator=g) * 0.05).half()
+  bias = (torch.randn(64 * r * r, generator=g) * 0.1).half() if epi == 3 else None
+  skip = torch.randn(n, h, w, 64, generator=g).half().cuda() if epi == 2 else None
+  ref = _conv_ref(x, wt.cuda(), None if bias is None else bias.cuda(), r, epi, 0.25, skip)
+  engine.set_conv_path(simt=False)
+  tc = _run_conv(engine, x, wt, bias, r, epi, 0.25, skip).float()
+  engine.set_conv_path(simt=True)
+  simt = _run_conv(engine, x, wt, bias, r, epi, 0.25, skip).float()
+  engine.set_conv_path(simt=False)
+  assert not torch.isnan(tc).any() and not torch.isnan(simt).any()
+  tol = 2.0 ** -10 * torch.clamp(ref.abs(), min=1.0) + 1e-4          # one fp16 ulp of the result + accumulation noise
+  assert ((tc - ref).abs() <= tol).all()
+  assert ((simt - ref).abs() <= tol).all()
+  # same rounding points, different fp32 summation order: equal up to one fp16 ulp on a small fraction
+  d = (tc - simt).abs()
+  assert (d <= 2.0 ** -10 * torch.clamp(ref.abs(), min=1.0)).all() and (d > 0).float().mean() < 0.05
+
+
+@pytest.mark.parametrize('name', H.case_names())
+def test_golden_cases_through_the_reference_api(engine, name):
+  c = H.load_case(name)
+  y = H.run_case_engine(c)                  # asserts the tile plan equals the reference's too
+  assert y.shape == c['ref'].shape
+  orc = H.run_case_oracle(c, mode='f16io')
+  assert np.abs(y - orc).max() <= 1e-3
+  d = np.abs(y - c['ref'])
+  assert H.psnr(y, c['ref']) >= 60.0
+  assert d.max() <= 1.5e-2 and np.quantile(d, .999) <= 4e-3
+  if c['alpha'] is not None:
+    assert np.array_equal(y[3], c['alpha'].astype(np.float16).astype(np.float32))
+
+
+@pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'dn15_tiled'])
+def test_simt_cross_check_path_agrees_with_tensor_core_path(engine, name):
+  c = H.load_case(name)
+  y_tc = H.run_case_engine(c)
+  engine.set_conv_path(simt=True)
+  try:
+    y_simt = H.run_case_engine(c)
+  finally:
+    engine.set_conv_path(simt=False)
+  assert np.abs(y_tc - y_simt).max() <= 1e-3
+
+
+def _sr_opt(key, scale, crop=0, ram=int(178 * 2 ** 30 * .9)):
+  from moephoto_b200 import runSR
+  from moephoto_b200.config import config
+  config.freeMemOverride, config.crop_sr = ram, (crop or 'auto')
+  try:
+    return runSR.getOpt({'model': 'a', 'scale': scale}, weights=H.load_weights(key))
+  finally:
+    config.crop_sr = 'auto'
+
+
+@pytest.mark.parametrize('key,scale,shape,crop', [('a2', 2, (3, 300, 420), 128), ('a4', 4, (3, 200, 333), 96), ('a3', 3, (2, 150, 260), 0)])
+def test_row_band_sharding_is_bit_exact(engine, key, scale, shape, crop):
+  """moe_run_plan's row window (what each GPU of a multi-GPU run computes) reproduces the full run exactly"""
+  from moephoto_b200 import imageProcess as IP, parallel as PAR
+  from moephoto_b200.config import config
+  opt = _sr_opt(key, scale, crop)
+  try:
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(5)).half().cuda()
+    full = IP.doCrop(opt, x)
+    for world in (2, 3, 8):
+      out = torch.full_like(full, float('nan'))
+      for rank in range(world):
+        lo, hi = PAR.band_rows(shape[1], scale, world, rank)
+        IP.run_plan(opt.modelCached, x, opt.plan, out, rows=(lo, hi))
+      assert torch.equal(out, full), world
+  finally:
+    config.freeMemOverride = None
+
+
+def test_full_size_properties_1080p_a2(engine):
+  """BASELINE configs[1] (1920x1080 -> 3840x2160, a2): determinism, sharding invariance on the real frame size,
+  the reference's single-tile auto plan, and tile-count independence within the seam tolerance"""
+  from moephoto_b200 import imageProcess as IP, parallel as PAR
+  from moephoto_b200.config import config
+  opt = _sr_opt('a2', 2)
+  try:
+    g = torch.Generator().manual_seed(11)
+    lo_res = torch.rand(3, 135, 240, generator=g)
+    x = torch.nn.functional.interpolate(lo_res[None], size=(1080, 1920), mode='bicubic')[0].clamp(0, 1).half().cuda()
+    y1 = IP.doCrop(opt, x)
+    assert len(opt.plan.tiles) == 1 and tuple(y1.shape) == (3, 2160, 3840)
+    assert torch.equal(y1, IP.doCrop(opt, x))
+    assert torch.isfinite(y1).all() and float(y1.min()) > -0.2 and float(y1.max()) < 1.2
+    out = torch.empty_like(y1)
+    for rank in range(4):
+      lo, hi = PAR.band_rows(1080, 2, 4, rank)
+      IP.run_plan(opt.modelCached, x, opt.plan, out, rows=(lo, hi))
+    assert torch.equal(out, y1)
+    # a 512-px crop gives 12 tiles; away from tile borders the receptive field (16 px) sees the same data
+    opt12 = _sr_opt('a2', 2, crop=512)
+    y12 = IP.doCrop(opt12, x)
+    assert len(opt12.plan.tiles) == 12
+    assert torch.equal(y12[:, 100:800, 100:800], y1[:, 100:800, 100:800])
+    assert 10 * np.log10(1.0 / float(((y12.float() - y1.float()) ** 2).mean())) > 60.0
+  finally:
+    config.freeMemOverride = None
+
+
+def test_bare_network_call_matches_oracle(engine):
+  """opt(x) on a (N,1,h,w) tile, like the reference's Option.__call__ (imageProcess.py:391-395)"""
+  from oracle import net as N
+  opt = _sr_opt('a4', 4)
+  from moephoto_b200.config import config
+  config.freeMemOverride = None
+  sd = H.load_weights('a4')
+  x = torch.rand(2, 1, 37, 53, generator=torch.Generator().manual_seed(2)).half()
+  y = opt(x.cuda())
+  assert tuple(y.shape) == (2, 1, 148, 212)
+  want = N.forward(sd, x.float().numpy(), mode='f16io')
+  assert np.abs(y.float().cpu().numpy() - want).max() <= 1e-3
+
+
+def test_frame_conversions_are_bit_exact(engine):
+  from oracle import tiling as T
+  from moephoto_b200 import imageProcess as IP
+  rng = np.random.default_rng(0)
+  img8 = rng.integers(0, 256, (37, 51, 3), dtype=np.uint8)
+  img16 = rng.integers(0, 65536, (37, 51, 3), dtype=np.uint16)
+  a = IP.toTorch(8)(img8)
+  assert np.array_equal(a.cpu().numpy(), T.to_planar(img8, 8, np.float16))
+  b = IP.toTorch(16)(img16)
+  assert np.array_equal(b.cpu().numpy(), T.to_planar(img16, 16, np.float16))
+  assert np.array_equal(IP.toTorch(8, swapRB=True)(img8).cpu().numpy(), T.to_planar(img8[:, :, ::-1], 8, np.float16))
+  y = torch.from_numpy(rng.uniform(-.1, 1.1, (3, 37, 51)).astype(np.float16)).cuda()
+  for bits in (8, 16):
+    got = IP.toOutput(bits)(y)
+    want = T.to_output(y.cpu().numpy(), bits)
+    assert np.array_equal(got.astype(np.int64), want.astype(np.int64) & (0xFFFF if bits == 16 else 0xFF))
+  assert np.array_equal(IP.toOutput(8)(IP.toFloat(y)), IP.toOutput(8)(y))      # accepts what toFloat hands over
+
+
+def test_strength_and_alpha(engine):
+  """RGBFilter with strength != 1 (strengthOp, imageProcess.py:562), fp16 rounding per op"""
+  from moephoto_b200 import runDN, imageProcess as IP
+  from moephoto_b200.config import config
+  config.freeMemOverride = int(4e9)
+  try:
+    opt = runDN.getOpt({'model': 'lite15', 'strength': 0.6}, weights=H.load_weights('dn_lite15'))
+    x = torch.rand(4, 50, 66, generator=torch.Generator().manual_seed(3)).half().cuda()
+    y = IP.RGBFilter(opt)(x)
+    opt1 = runDN.getOpt({'model': 'lite15'}, weights=H.load_weights('dn_lite15'))
+    y1 = IP.RGBFilter(opt1)(x)
+    h16 = lambda t: t.half().float()
+    want = h16(h16(0.6 * y1[:3].float()) + h16(np.float32(1 - 0.6) * x[:3].float()))
+    assert torch.equal(y[:3].float(), want) and torch.equal(y[3], x[3])
+  finally:
+    config.freeMemOverride = None
+
+
+def test_ensemble_is_the_average_of_the_dihedral_passes(engine):
+  from moephoto_b200 import runSR, imageProcess as IP
+  from moephoto_b200.config import config
+  config.freeMemOverride = int(4e9)
+  try:
+    sd = H.load_weights('a2')
+    x = torch.rand(3, 48, 72, generator=torch.Generator().manual_seed(4)).half().cuda()
+    o0 = runSR.getOpt({'model': 'a', 'scale': 2, 'ensemble': 0}, weights=sd)
+    o3 = runSR.getOpt({'model': 'a', 'scale': 2, 'ensemble': 3}, weights=sd)
+    y3 = runSR.sr(o3)(x)
+    f = lambda t: IP.doCrop(o0, t.contiguous())
+    ot = runSR.getOpt({'model': 'a', 'scale': 2}, weights=sd)
+    ft = lambda t: IP.doCrop(ot, t.contiguous())
+    want = f(x) + ft(x.transpose(-1, -2)).transpose(-1, -2) + f(x.flip(-1)).flip(-1) + f(x.flip(-1, -2)).flip(-1, -2)
+    assert torch.allclose(y3.float(), (want / 4).float(), atol=2e-3)
+  finally:
+    config.freeMemOverride = None
+
+
+def test_host_buffer_entry_point_equals_the_api_path(engine):
+  """moe_enhance_host (uint8 host frame in, uint8 host frame out) == toTorch -> doCrop -> toOutput"""
+  from moephoto_b200 import _lib, imageProcess as IP
+  from moephoto_b200.config import config
+  opt = _sr_opt('a2', 2, crop=64, ram=int(4e9))
+  try:
+    img = np.random.default_rng(9).integers(0, 256, (90, 130, 3), dtype=np.uint8)
+    want = IP.toOutput(8)(IP.doCrop(opt, IP.toTorch(8)(img)))
+    out = np.empty((180, 260, 3), dtype=np.uint8)
+    _lib.check(engine.lib.moe_enhance_host(opt.modelCached.handle, img.ctypes.data_as(ctypes.c_void_p), 8, ctypes.byref(opt.plan.c),
+                                           out.ctypes.data_as(ctypes.c_void_p), 8, None))
+    assert np.array_equal(out, want)
+  finally:
+    config.freeMemOverride = None
+
+
+def test_errors_are_status_codes_not_crashes(engine):
+  from moephoto_b200 import _lib, imageProcess as IP
+  opt = _sr_opt('a2', 2, ram=int(4e9))
+  from moephoto_b200.config import config
+  config.freeMemOverride = None
+  x = torch.rand(3, 40, 40).half().cuda()
+  with pytest.raises(ValueError):
+    IP.run_plan(opt.modelCached, x, IP.TilePlan.single(40, 40, 4))          # scale mismatch
+  with pytest.raises(ValueError):
+    IP.run_plan(opt.modelCached, x, IP.TilePlan.single(48, 40, 2))          # shape mismatch
+  bad = IP.TilePlan([(0, 400, 0, 40, 0, 0, 800, 80)], 2, 0, 40, 40, 0, 0, np.zeros(1, np.float32))
+  with pytest.raises(ValueError):
+    IP.run_plan(opt.modelCached, x, bad)                                     # tile outside the image
+  h = ctypes.c_void_p()
+  assert engine.lib.moe_model_load(engine.handle, 2, b'garbage-garbage-garbage-garbage-garbage', 40, ctypes.byref(h)) == _lib.MOE_ERR_INVALID
+  with pytest.raises(MemoryError):
+    cfgopt = _sr_opt('a2', 2, ram=1000)
+    IP.doCrop(cfgopt, x)
+  config.freeMemOverride = None
