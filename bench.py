@@ -70,6 +70,24 @@ def synthetic_frame(h, w, seed=0):
   return np.ascontiguousarray((img * 255).round().astype(np.uint8))
 
 
+def host_threads():
+  """cores this process may really use: affinity mask, capped by the cgroup CPU quota"""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+  try:
+    q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+    if q != 'max':
+      n = max(1, min(n, int(float(q) / float(per))))
+  except Exception:
+    try:
+      q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+      per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+      if q > 0:
+        n = max(1, min(n, q // per))
+    except Exception:
+      pass
+  return n
+
+
 def peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -139,7 +157,7 @@ def run_reference(args, rank):
   if rank != 0:
     return
   import torch
-  threads = os.cpu_count() or 1
+  threads = host_threads()
   torch.set_num_threads(threads)
   sd, wsrc = a4_weights()
   crop = synthetic_frame(CPU_SAMPLE, CPU_SAMPLE, 1)
@@ -300,7 +318,7 @@ def main():
   }
   if world == 1 and not args.no_cpu_baseline:
     import torch as _t
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     _t.set_num_threads(threads)
     crop = synthetic_frame(CPU_SAMPLE, CPU_SAMPLE, 1)
     cpu_port_step(sd, crop, threads)

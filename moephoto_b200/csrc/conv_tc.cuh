@@ -2,7 +2,7 @@
 //
 // One persistent CTA per SM walks DOWN a 128-pixel-wide column strip of one image plane:
 //   * M tile   = one output row segment of 128 pixels (TMEM lane = pixel, column = output channel)
-//   * K        = 9 taps x 64 input channels = 36 tcgen05.mma of 128 x (64*NCH) x 16
+//   * K        = 9 taps x 64 input channels = 36 tcgen05.mma of 128 x 64 x 16
 //   * A operand= the input rows y-1, y, y+1, each TMA-loaded ONCE (130 px x 128 B, 128-byte swizzle)
 //                into a ring of row slots; the nine taps are nine *views* of those three slots: the
 //                smem descriptor's start address is moved by dx*128 B (next pixel) and k*32 B (next
@@ -10,13 +10,16 @@
 //                (Measured on B200, profiles/r01_diag_first_contact.log: the 128B swizzle is a function
 //                of the absolute smem address, so a start address that is not 1024-aligned needs NO
 //                base_offset in the descriptor; setting base_offset = (addr>>7)&7 gives garbage.)
-//   * B operand= the layer's weights for NCH 64-channel output chunks, resident in smem for the whole
+//   * B operand= the layer's weights for one 64-channel output chunk, resident in smem for the whole
 //                kernel (pre-swizzled on the host, fetched with cp.async.bulk).
 //   * zero padding at the tile border is TMA out-of-bounds fill (x = -1, x = W, y = -1, y = H).
-//   * epilogue = 4 warps: tcgen05.ld -> PReLU | x scale + skip | + bias, PReLU -> fp16 -> 128-byte pixel
-//                stores; PixelShuffle is only an address computation (chunk q = (i,j) -> pixel
-//                (y*r+i, x*r+j)), see weights.py for the matching output-channel permutation.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = epilogue.
+//   * epilogue = 8 warps (2 per TMEM lane quadrant, 32 channels each): tcgen05.ld -> PReLU | x scale +
+//                skip | + bias, PReLU -> fp16 -> a swizzled 128 px x 128 B staging tile in smem -> ONE TMA
+//                tensor store per row.  The residual operand arrives the same way (TMA load into the
+//                staging tile, updated in place).  PixelShuffle is the store's tensor map: chunk q = (i,j)
+//                owns the view out[:, i::r, j::r, :] (weights.py permutes the output channels to match).
+//                Right-edge clipping is the TMA store's bounds check.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..9 = epilogue.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -30,9 +33,9 @@ enum ConvEpilogue : int { EPI_PLAIN = 0, EPI_PRELU = 1, EPI_SCALE_SKIP = 2, EPI_
 struct ConvParams {
   const uint8_t* w_img;   // [r*r chunks][9 taps][64 rows][128 B], 128B-swizzled fp16
   const float* bias;      // [r*r][64] or nullptr
-  const __half* in;       // NHWC (N,H,W,64)   (tcgen05 path reads it through the tensor map)
+  const __half* in;       // NHWC (N,H,W,64)   (the tcgen05 path reads it through the tensor map)
   __half* out;            // NHWC (N,H*r,W*r,64)
-  const __half* skip;     // NHWC (N,H,W,64) when epi == EPI_SCALE_SKIP
+  const __half* skip;     // NHWC (N,H,W,64) when epi == EPI_SCALE_SKIP (may alias out)
   int N, H, W;
   int r;                  // 1, 2 or 3
   int epi;
@@ -40,21 +43,29 @@ struct ConvParams {
   int strips, nseg, seg_rows, items;
 };
 
+struct ConvMaps {
+  CUtensorMap in;         // (64, W, H, N), box (64,130,1,1)
+  CUtensorMap skip;       // (64, W, H, N), box (64,128,1,1)   (EPI_SCALE_SKIP only)
+  CUtensorMap out[9];     // chunk q = (i,j): the (64, W, H, N) view out[:, i::r, j::r, :], box (64,128,1,1)
+};
+
 constexpr int kStripW = 128;
 constexpr int kRowPx = kStripW + 2;
-constexpr uint32_t kRowBytes = kRowPx * 128;          // 16640, the TMA box
+constexpr uint32_t kRowBytes = kRowPx * 128;          // 16640, the input TMA box
 constexpr uint32_t kSlotBytes = 17 * 1024;            // row slot, 1024-aligned for the swizzle pattern
 constexpr uint32_t kChunkImgBytes = 9 * 64 * 128;     // 73728
-constexpr int kConvThreads = 192;
+constexpr uint32_t kStageBytes = kStripW * 128;       // 16384: one output row segment
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kConvThreads = 64 + kEpiThreads;        // 320
 
-template <int NCH> struct ConvCfg {
-  static constexpr int kSlots = NCH == 1 ? 8 : 4;
+struct ConvCfg {
+  static constexpr int kSlots = 6;
   static constexpr int kAccStages = 4;
-  static constexpr int kN = 64 * NCH;
-  static constexpr uint32_t kTmemCols = kAccStages * kN;
-  static constexpr uint32_t kWBytes = NCH * kChunkImgBytes;
+  static constexpr int kOutStages = 2;
+  static constexpr uint32_t kTmemCols = kAccStages * 64;
   static constexpr uint32_t kBarBytes = 1024;
-  static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kWBytes + kBarBytes;
+  static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kChunkImgBytes + kOutStages * kStageBytes + kBarBytes;
 };
 
 __device__ __forceinline__ void conv_decode_item(const ConvParams& p, int item, int ncg, int& n, int& x0, int& y0, int& y1) {
@@ -75,35 +86,37 @@ __device__ __forceinline__ float epi_apply(float v, int epi, float param, float 
   return v;
 }
 
-template <int NCH>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams p)
+conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
 {
-  using Cfg = ConvCfg<NCH>;
-  constexpr int S = Cfg::kSlots, AS = Cfg::kAccStages, NN = Cfg::kN;
+  using Cfg = ConvCfg;
+  constexpr int S = Cfg::kSlots, AS = Cfg::kAccStages, OS = Cfg::kOutStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t ring = base;
-  const uint32_t wsm = base + S * kSlotBytes;
-  const uint32_t bars = wsm + Cfg::kWBytes;
-  const uint32_t full = bars, empty = bars + 8 * S, tfull = bars + 16 * S, tempty = tfull + 8 * AS;
-  const uint32_t wbar = tempty + 8 * AS;
-  const uint32_t tslot = wbar + 8;
+  const uint32_t wsm = ring + S * kSlotBytes;
+  const uint32_t stg = wsm + kChunkImgBytes;                       // OS staging tiles, 1024-aligned
+  const uint32_t bars = stg + OS * kStageBytes;
+  const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
+  const uint32_t skfull = tempty + 8 * AS, wbar = skfull + 8 * OS, tslot = wbar + 8;
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
+  uint8_t* stg_ptr = smem + (stg - base);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nchunks = p.r * p.r;
-  const int ncg = nchunks / NCH;                 // chunk groups; gridDim.x % ncg == 0 (host guarantees)
-  const int cg = blockIdx.x % ncg;
+  const int ncg = p.r * p.r;                     // one chunk per CTA; gridDim.x % ncg == 0 (host guarantees)
+  const int chunk = blockIdx.x % ncg;
+  const CUtensorMap* omap = &maps.out[chunk];
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
-    for (int i = 0; i < AS; ++i) { ptx::mbar_init(tfull + 8 * i, 1); ptx::mbar_init(tempty + 8 * i, 128); }
+    for (int i = 0; i < AS; ++i) { ptx::mbar_init(tfull + 8 * i, 1); ptx::mbar_init(tempty + 8 * i, kEpiThreads); }
+    for (int i = 0; i < OS; ++i) ptx::mbar_init(skfull + 8 * i, 1);
     ptx::mbar_init(wbar, 1);
     ptx::fence_mbar_init();
-    ptx::prefetch_tmap(&in_map);
+    ptx::prefetch_tmap(&maps.in);
+    ptx::prefetch_tmap(omap);
   }
   if (warp == 1) ptx::tmem_alloc(tslot, Cfg::kTmemCols);
   ptx::tc_fence_before_sync();
@@ -114,12 +127,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams p
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      ptx::mbar_expect_tx(wbar, Cfg::kWBytes);
-      for (int c = 0; c < NCH; ++c) {
-        const uint8_t* src = p.w_img + static_cast<size_t>(cg * NCH + c) * kChunkImgBytes;
-        for (int tap = 0; tap < 9; ++tap)
-          ptx::bulk_load_1d(wsm + tap * (NCH * 8192) + c * 8192, src + tap * 8192, 8192, wbar);
-      }
+      ptx::mbar_expect_tx(wbar, kChunkImgBytes);
+      const uint8_t* src = p.w_img + static_cast<size_t>(chunk) * kChunkImgBytes;
+      for (int tap = 0; tap < 9; ++tap) ptx::bulk_load_1d(wsm + tap * 8192, src + tap * 8192, 8192, wbar);
       uint32_t ld = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         int n, x0, y0, y1;
@@ -128,14 +138,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams p
           const uint32_t slot = ld % S;
           ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
           ptx::mbar_expect_tx(full + 8 * slot, kRowBytes);
-          ptx::tma_load_4d(ring + slot * kSlotBytes, &in_map, full + 8 * slot, 0, x0 - 1, yy, n);
+          ptx::tma_load_4d(ring + slot * kSlotBytes, &maps.in, full + 8 * slot, 0, x0 - 1, yy, n);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_f16_f32(128, NN);
+      constexpr uint32_t idesc = ptx::idesc_f16_f32(128, 64);
+      const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
+      const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
       ptx::mbar_wait(wbar, 0);
       ptx::tc_fence_after_sync();
       uint32_t cons = 0, acc = 0;
@@ -151,18 +163,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams p
           const uint32_t stage = acc % AS;
           ptx::mbar_wait(tempty + 8 * stage, ((acc / AS) & 1) ^ 1);
           ptx::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + stage * NN;
+          const uint32_t d_tmem = tmem_base + stage * 64;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t abase = ring + ((cons + j + dy) % S) * kSlotBytes;
+            // the descriptor's address field counts 16-byte units: slot = 1088, pixel = 8, 16 channels = 2, tap = 512
+            const uint64_t arow = adesc0 + static_cast<uint64_t>(((cons + j + dy) % S) * (kSlotBytes >> 4));
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              const uint32_t a0 = abase + dx * 128;
-              const uint32_t b0 = wsm + (dy * 3 + dx) * (NCH * 8192);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a0 + k * 32, 1024, 0),
-                                ptx::smem_desc_sw128(b0 + k * 32, 1024, 0), idesc, (dy | dx | k) != 0);
+                ptx::mma_f16_ss(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, (dy | dx | k) != 0);
               }
             }
           }
@@ -179,75 +189,97 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvParams p
       ptx::mbar_wait(wbar, 1);
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int lgrp = warp & 3;                       // TMEM lanes this warp may read: 32*lgrp ..
-    const int L = lgrp * 32 + lane;
-    const int Ho = p.H * p.r, Wo = p.W * p.r;
-    uint32_t acc = 0;
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int lgrp = warp & 3;                       // TMEM lanes this warp may read: 32*lgrp .. +31
+    const int half = (warp - 2) >> 2;                // which 32 of the 64 channels
+    const int L = lgrp * 32 + lane;                  // pixel within the strip == staging row
+    const bool leader = (tid == 64);
+    const bool has_skip = p.epi == EPI_SCALE_SKIP;
+    uint8_t* my_row = stg_ptr + L * 128;
+    const int sw = L & 7;
+    float bias_r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias_r[j] = p.epi == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
+
+    uint32_t acc = 0;                                // output-row counter over ALL items
+    if (has_skip && leader && blockIdx.x < p.items) { // residual tile of the very first row
+      int n, x0, y0, y1;
+      conv_decode_item(p, blockIdx.x, ncg, n, x0, y0, y1);
+      ptx::mbar_expect_tx(skfull, kStageBytes);
+      ptx::tma_load_4d(stg, &maps.skip, skfull, 0, x0, y0, n);
+    }
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int n, x0, y0, y1;
       conv_decode_item(p, item, ncg, n, x0, y0, y1);
-      const int x = x0 + L;
-      const bool valid = x < p.W;
       for (int y = y0; y < y1; ++y, ++acc) {
         const uint32_t stage = acc % AS;
+        const uint32_t os = acc % OS;
+        uint8_t* row = my_row + os * kStageBytes;
+        // (1) staging tile `os`: free (its previous TMA store has read it) or holding the residual
+        if (has_skip) {
+          ptx::mbar_wait(skfull + 8 * os, (acc / OS) & 1);
+        } else {
+          if (leader) ptx::bulk_wait_read<OS - 1>();
+          ptx::named_bar_sync(1, kEpiThreads);
+        }
+        // (2) accumulator -> registers, TMEM stage back to the MMA warp
         ptx::mbar_wait(tfull + 8 * stage, (acc / AS) & 1);
         ptx::tc_fence_after_sync();
-        const size_t ipix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 64 + half * 32, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(tempty + 8 * stage);
+        // (3) epilogue math, fp16 pack, swizzled staging write (16-byte chunk c of row L sits at c ^ (L & 7))
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int chunk = cg * NCH + c;
-          const int sy = chunk / p.r, sx = chunk - sy * p.r;
-          const size_t opix = (static_cast<size_t>(n) * Ho + (y * p.r + sy)) * Wo + (x * p.r + sx);
+        for (int q = 0; q < 4; ++q) {
+          const int cidx = ((half * 4 + q) ^ sw) << 4;
+          uint4 sk = make_uint4(0, 0, 0, 0);
+          if (has_skip) sk = *reinterpret_cast<const uint4*>(row + cidx);
+          uint32_t w[4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * NN + c * 64 + h * 32, v);
-            ptx::tmem_ld_wait();
-            if (c == NCH - 1 && h == 1) {            // last read of this stage: hand TMEM back to the MMA warp
-              ptx::tc_fence_before_sync();
-              ptx::mbar_arrive(tempty + 8 * stage);
+          for (int e = 0; e < 4; ++e) {
+            const int j = q * 8 + e * 2;
+            float s0 = 0.f, s1 = 0.f;
+            if (has_skip) {
+              const uint32_t sw32 = reinterpret_cast<const uint32_t*>(&sk)[e];
+              const __half2 hs = *reinterpret_cast<const __half2*>(&sw32);
+              s0 = __low2float(hs);
+              s1 = __high2float(hs);
             }
-            if (valid) {
-              uint4 sk[4];
-              if (p.epi == EPI_SCALE_SKIP) {
-                const uint4* sp = reinterpret_cast<const uint4*>(p.skip + ipix * 64 + h * 32);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) sk[q] = sp[q];   // plain loads: `skip` may alias `out`
-              }
-              uint4 o[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = q * 8 + e * 2;
-                  float b0 = 0.f, b1 = 0.f, s0 = 0.f, s1 = 0.f;
-                  if (p.epi == EPI_BIAS_PRELU) {
-                    b0 = __ldg(p.bias + chunk * 64 + h * 32 + j);
-                    b1 = __ldg(p.bias + chunk * 64 + h * 32 + j + 1);
-                  }
-                  if (p.epi == EPI_SCALE_SKIP) {
-                    const uint32_t sw = reinterpret_cast<const uint32_t*>(&sk[q])[e];
-                    const __half2 hs = *reinterpret_cast<const __half2*>(&sw);
-                    s0 = __low2float(hs);
-                    s1 = __high2float(hs);
-                  }
-                  const float f0 = epi_apply(__uint_as_float(v[j]), p.epi, p.param, b0, s0);
-                  const float f1 = epi_apply(__uint_as_float(v[j + 1]), p.epi, p.param, b1, s1);
-                  const __half2 hv = __floats2half2_rn(f0, f1);
-                  w[e] = *reinterpret_cast<const uint32_t*>(&hv);
-                }
-                o[q] = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-              uint4* dp = reinterpret_cast<uint4*>(p.out + opix * 64 + h * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dp[q] = o[q];
+            const float f0 = epi_apply(__uint_as_float(v[j]), p.epi, p.param, bias_r[j], s0);
+            const float f1 = epi_apply(__uint_as_float(v[j + 1]), p.epi, p.param, bias_r[j + 1], s1);
+            const __half2 hv = __floats2half2_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          *reinterpret_cast<uint4*>(row + cidx) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        // (4) hand the tile to the async proxy and store it
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(2, kEpiThreads);
+        if (leader) {
+          ptx::tma_store_4d(omap, stg + os * kStageBytes, 0, x0, y, n);
+          ptx::bulk_commit();
+          if (has_skip) {
+            // residual tile of the NEXT row goes into the other staging tile once that tile's store has read it
+            int nn = n, nx0 = x0, ny = y + 1;
+            bool more = true;
+            if (ny >= y1) {
+              const int nitem = item + gridDim.x;
+              more = nitem < p.items;
+              if (more) { int t1; conv_decode_item(p, nitem, ncg, nn, nx0, ny, t1); }
+            }
+            if (more) {
+              const uint32_t nos = (acc + 1) % OS;
+              ptx::bulk_wait_read<OS - 1>();            // every store but the one just issued has read its tile
+              ptx::mbar_expect_tx(skfull + 8 * nos, kStageBytes);
+              ptx::tma_load_4d(stg + nos * kStageBytes, &maps.skip, skfull + 8 * nos, 0, nx0, ny, nn);
             }
           }
         }
       }
     }
+    if (leader) ptx::bulk_wait<0>();                     // all stores complete before the CTA exits
   }
   __syncwarp();
   ptx::tc_fence_before_sync();

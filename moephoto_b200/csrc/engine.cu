@@ -17,6 +17,7 @@
 #include "blob.h"
 #include "conv_tc.cuh"
 #include "kernels_simt.cuh"
+#include "head_tc.cuh"
 
 using namespace moe;
 
@@ -58,7 +59,7 @@ struct MoeEngine {
   std::atomic<int64_t> launches{0};
   int simt = 0;
   int cur_feat = 64;       // real filter count of the model being run (48 for NetDN) — FLOP accounting only
-  bool smem_attr_set = false;
+  bool smem_attr_set = false, head_attr_set = false;
   // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3, 2 heads, 3 frame I/O
   bool profiling = false;
   struct Span { int cls; cudaEvent_t a, b; double work; };
@@ -80,6 +81,7 @@ struct MoeModel {
   const uint8_t* up_img[4] = {nullptr, nullptr, nullptr, nullptr};
   const float* up_bias[4] = {nullptr, nullptr, nullptr, nullptr};
   const float* head_w[2] = {nullptr, nullptr};
+  uint8_t* d_head_img = nullptr;   // [2][16 rows][128 B] swizzled fp16 image of the two head filters (head_tc.cuh)
 };
 
 namespace {
@@ -150,21 +152,73 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   p.items = static_cast<int>(items);
   const int grid = static_cast<int>(std::min<int64_t>(G, items));   // items is a multiple of ncg
 
-  CUtensorMap tmap;
-  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
-  const cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(W) * 128, static_cast<cuuint64_t>(W) * H * 128};
-  const cuuint32_t box[4] = {64, kRowPx, 1, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = e->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d H=%d W=%d", (int)cr, N, H, W);
+  // tensor maps: input rows (130-px box), residual rows and one output view per PixelShuffle sub-pixel
+  ConvMaps maps;
+  memset(&maps, 0, sizeof maps);
+  auto encode = [&](CUtensorMap* tm, const void* ptr, cuuint64_t w, cuuint64_t h, cuuint64_t n, cuuint64_t pix_stride,
+                    cuuint64_t row_stride, cuuint64_t plane_stride, cuuint32_t box_w) -> CUresult {
+    const cuuint64_t dims[4] = {64, w, h, n};
+    const cuuint64_t strides[3] = {pix_stride, row_stride, plane_stride};
+    const cuuint32_t box[4] = {64, box_w, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  const cuuint64_t uW = W, uH = H, uN = N, Wo = static_cast<cuuint64_t>(W) * r, Ho = static_cast<cuuint64_t>(H) * r;
+  CUresult cr = encode(&maps.in, in, uW, uH, uN, 128, uW * 128, uW * uH * 128, kRowPx);
+  if (cr == CUDA_SUCCESS && epi == EPI_SCALE_SKIP) cr = encode(&maps.skip, skip, uW, uH, uN, 128, uW * 128, uW * uH * 128, kStripW);
+  for (int q = 0; q < r * r && cr == CUDA_SUCCESS; ++q) {
+    const int sy = q / r, sx = q % r;
+    cr = encode(&maps.out[q], out + (static_cast<size_t>(sy) * Wo + sx) * 64, uW, uH, uN, static_cast<cuuint64_t>(r) * 128,
+                static_cast<cuuint64_t>(r) * Wo * 128, Ho * Wo * 128, kStripW);
+  }
+  if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d H=%d W=%d r=%d", (int)cr, N, H, W, r);
   if (!e->smem_attr_set) {
-    MOE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<1>::kSmemBytes));
+    MOE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg::kSmemBytes));
     e->smem_attr_set = true;
   }
-  conv3x3_tc_kernel<1><<<grid, kConvThreads, ConvCfg<1>::kSmemBytes, st>>>(tmap, p);
+  conv3x3_tc_kernel<<<grid, kConvThreads, ConvCfg::kSmemBytes, st>>>(maps, p);
   return check_launch(e, "conv3x3_tc_kernel");
+}
+
+// ---- the two heads + blend + store on the tensor cores (head_tc.cuh) ---------------------------
+int launch_head_tc(MoeEngine* e, cudaStream_t st, const MoeModel* m, const HeadParams& hp)
+{
+  HeadTcParams p{};
+  p.g = hp;
+  p.w_img = m->d_head_img;
+  p.strips = (hp.W + kHeadStripOut - 1) / kHeadStripOut;
+  const int G = e->sm_count;
+  const int64_t base_items = static_cast<int64_t>(hp.N) * p.strips;
+  int nseg = static_cast<int>((4ll * G + base_items - 1) / base_items);
+  nseg = std::max(1, std::min(nseg, std::max(1, hp.H / 16)));
+  p.seg_rows = (hp.H + nseg - 1) / nseg;
+  p.nseg = (hp.H + p.seg_rows - 1) / p.seg_rows;
+  const int64_t items = base_items * p.nseg;
+  if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "head problem too large");
+  p.items = static_cast<int>(items);
+  HeadMaps maps;
+  memset(&maps, 0, sizeof maps);
+  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(hp.W), static_cast<cuuint64_t>(hp.H), static_cast<cuuint64_t>(hp.N)};
+  const cuuint64_t strides[3] = {128, dims[1] * 128, dims[1] * dims[2] * 128};
+  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int b = 0; b < 2; ++b) {
+    CUresult cr = e->encode(b ? &maps.r : &maps.u, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(b ? hp.r : hp.u), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the head input", (int)cr);
+  }
+  if (!e->head_attr_set) {
+    MOE_CUDA(cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmemBytes));
+    e->head_attr_set = true;
+  }
+  {
+    Timed timed(e, st, 2, static_cast<double>(hp.N) * hp.H * hp.W * (2 * 128 + 2));   // bytes: two 64-ch fp16 reads, one fp16 write
+    head_tc_kernel<<<static_cast<int>(std::min<int64_t>(G, items)), kHeadThreads, kHeadSmemBytes, st>>>(maps, p);
+  }
+  return MOE_OK;
 }
 
 // ---- geometry of one tile restricted to a canvas row window ------------------------------------
@@ -353,6 +407,21 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
   for (int b = 0; b < 2 && complete; ++b)
     for (uint32_t s = 0; s < h.n_up; ++s) complete = m->up_img[2 * b + s] && m->up_bias[2 * b + s];
   if (!complete) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "blob is missing sections"); }
+  {
+    // head filters as a K-major SWIZZLE_128B B operand: row = tap (9 of 16 used), 64 input channels
+    std::vector<__half> img(2 * 16 * 64, __float2half(0.f));
+    for (int b = 0; b < 2; ++b) {
+      const float* hw = reinterpret_cast<const float*>(hb + (reinterpret_cast<const uint8_t*>(m->head_w[b]) - m->d_blob));
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < 64; ++c)
+          img[(b * 16 + t) * 64 + (((c >> 3) ^ (t & 7)) << 3) + (c & 7)] = __float2half(hw[t * 64 + c]);
+    }
+    if (cudaMalloc(&m->d_head_img, 4096) != cudaSuccess ||
+        cudaMemcpy(m->d_head_img, img.data(), 4096, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError(); cudaFree(m->d_blob); delete m;
+      return fail(MOE_ERR_NOMEM, "head weight upload failed");
+    }
+  }
   *out = m;
   return MOE_OK;
 }
@@ -362,6 +431,7 @@ void moe_model_free(MoeModel* m)
   if (!m) return;
   Guard g(m->e->device);
   if (m->d_blob) cudaFree(m->d_blob);
+  if (m->d_head_img) cudaFree(m->d_head_img);
   delete m;
 }
 
@@ -461,11 +531,13 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     for (int i = 0; i < plan->pad_sc; ++i) hp.ramp[i] = plan->ramp[i];
     hp.canvas = static_cast<__half*>(canvas);
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
-    dim3 hgrid((hp.W + 127) / 128, hp.H, N);
-    if (hgrid.y > 65535u || hgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the head kernel grid");
-    {
-    Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (2 * 128 + 2));   // bytes: two 64-ch fp16 reads, one fp16 write
-    head_blend_kernel<<<hgrid, 128, 0, st>>>(hp);
+    if (e->simt) {
+      dim3 hgrid((hp.W + 127) / 128, hp.H, N);
+      if (hgrid.y > 65535u || hgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the head kernel grid");
+      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (2 * 128 + 2));   // bytes: two 64-ch fp16 reads, one fp16 write
+      head_blend_kernel<<<hgrid, 128, 0, st>>>(hp);
+    } else {
+      if ((rc = launch_head_tc(e, st, m, hp)) != MOE_OK) return rc;
     }
     if ((rc = check_launch(e, "head_blend_kernel")) != MOE_OK) return rc;
   }

@@ -69,10 +69,10 @@ def run_conv(eng, x, w, bias, r, epi, param, skip):
 
 def conv_suite(eng):
   g = torch.Generator(device='cpu').manual_seed(0)
-  cases = [(1, 8, 128, 1, 0), (1, 20, 128, 1, 1), (2, 33, 200, 1, 2), (3, 40, 48, 1, 1), (1, 17, 300, 2, 3), (1, 12, 130, 3, 3),
+  cases = [(1, 1, 1, 1, 0), (1, 300, 127, 1, 2), (1, 8, 128, 1, 0), (1, 20, 128, 1, 1), (2, 33, 200, 1, 2), (3, 40, 48, 1, 1), (1, 17, 300, 2, 3), (1, 12, 130, 3, 3),
            (3, 70, 257, 1, 0)]
-  for mode_name, simt, bom in (('simt', True, False), ('tc/base_offset=0', False, False), ('tc/base_offset=addr', False, True)):
-    eng.set_conv_path(simt=simt, base_offset_mode=bom)
+  for mode_name, simt in (('simt', True), ('tc', False)):
+    eng.set_conv_path(simt=simt)
     for (n, h, wd, r, epi) in cases:
       try:
         x = (torch.randn(n, h, wd, 64, generator=g) * 0.5).half().cuda()
@@ -89,7 +89,7 @@ def conv_suite(eng):
         say('[conv %-20s] n=%d h=%d w=%d r=%d epi=%d  EXCEPTION %r' % (mode_name, n, h, wd, r, epi, ex))
         if 'launch' in str(ex).lower() or 'cuda' in str(ex).lower():
           return False
-  eng.set_conv_path(False, False)
+  eng.set_conv_path(False)
   return True
 
 
@@ -127,10 +127,15 @@ def timing(eng):
         y = runSR.sr(opt)(x)
       torch.cuda.synchronize()
       t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+      eng.profile(True)
       t0.record()
       for _ in range(3):
         y = runSR.sr(opt)(x)
       t1.record(); torch.cuda.synchronize()
+      eng.profile(False)
+      pr = eng.profile_read()
+      say('[prof] %s' % key, {k: '%.2f ms/frame, %d launches' % (v[0] / 3, v[2] // 3) for k, v in pr.items()},
+          'conv TFLOP/s %.0f' % (pr['conv3x3'][1] / (pr['conv3x3'][0] * 1e-3) / 1e12), 'head GB/s %.0f' % (pr['head'][1] / (pr['head'][0] * 1e-3) / 1e9))
       ms = t0.elapsed_time(t1) / 3
       say('[time] %s %s tiles=%d  %.2f ms/frame  %.1f MPix/s out' % (key, shape, len(opt.plan.tiles), ms, y.shape[1] * y.shape[2] / ms / 1e3))
       del y, x, opt
