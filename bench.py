@@ -105,10 +105,18 @@ class ClockSampler:
     self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
     self.p = None
     try:
-      self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+      self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '50'],
                                 stdout=self.f, stderr=subprocess.DEVNULL)
     except Exception:
       pass
+
+  def mark(self):
+    """samples written before this call belong to the warm-up and are dropped"""
+    self.f.flush()
+    try:
+      self.skip = sum(1 for _ in open(self.f.name))
+    except Exception:
+      self.skip = 0
 
   def stop(self):
     out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
@@ -120,7 +128,7 @@ class ClockSampler:
     except Exception:
       self.p.kill()
     self.f.flush()
-    rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+    rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()][getattr(self, 'skip', 0):]
     os.unlink(self.f.name)
     sm, reasons = [], set()
     for r in rows:
@@ -243,12 +251,14 @@ def main():
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return ms.item(), r
 
+  sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~1 s to begin sampling
   for _ in range(args.warmup):
     y = step()
   sync()
   plan = opt.plan
   l0 = eng.launches()
-  sampler = ClockSampler(local) if rank == 0 else None
+  if sampler:
+    sampler.mark()
   eng.profile(True)
   total_ms, y = timed(step, args.steps)
   eng.profile(False)

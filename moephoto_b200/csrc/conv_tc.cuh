@@ -125,49 +125,56 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   const uint32_t tmem_base = *tslot_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp converged, one lane issues)
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, kChunkImgBytes);
       const uint8_t* src = p.w_img + static_cast<size_t>(chunk) * kChunkImgBytes;
       for (int tap = 0; tap < 9; ++tap) ptx::bulk_load_1d(wsm + tap * 8192, src + tap * 8192, 8192, wbar);
-      uint32_t ld = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int n, x0, y0, y1;
-        conv_decode_item(p, item, ncg, n, x0, y0, y1);
-        for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
-          const uint32_t slot = ld % S;
-          ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
+    }
+    __syncwarp();
+    uint32_t ld = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, x0, y0, y1;
+      conv_decode_item(p, item, ncg, n, x0, y0, y1);
+      for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
+        const uint32_t slot = ld % S;
+        ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_expect_tx(full + 8 * slot, kRowBytes);
           ptx::tma_load_4d(ring + slot * kSlotBytes, &maps.in, full + 8 * slot, 0, x0 - 1, yy, n);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_f16_f32(128, 64);
-      const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
-      const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
-      ptx::mbar_wait(wbar, 0);
-      ptx::tc_fence_after_sync();
-      uint32_t cons = 0, acc = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int n, x0, y0, y1;
-        conv_decode_item(p, item, ncg, n, x0, y0, y1);
-        const int nrows = y1 - y0;
-        ptx::mbar_wait(full + 8 * (cons % S), (cons / S) & 1);
-        ptx::mbar_wait(full + 8 * ((cons + 1) % S), ((cons + 1) / S) & 1);
-        for (int j = 0; j < nrows; ++j) {
-          const uint32_t l2 = cons + j + 2;
-          ptx::mbar_wait(full + 8 * (l2 % S), (l2 / S) & 1);
-          const uint32_t stage = acc % AS;
-          ptx::mbar_wait(tempty + 8 * stage, ((acc / AS) & 1) ^ 1);
-          ptx::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + stage * 64;
+    // ------------------------------------------------------------ MMA issuer (whole warp converged, one lane issues)
+    constexpr uint32_t idesc = ptx::idesc_f16_f32(128, 64);
+    const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
+    const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
+    ptx::mbar_wait(wbar, 0);
+    ptx::tc_fence_after_sync();
+    uint32_t cons = 0, acc = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, x0, y0, y1;
+      conv_decode_item(p, item, ncg, n, x0, y0, y1);
+      const int nrows = y1 - y0;
+      ptx::mbar_wait(full + 8 * (cons % S), (cons / S) & 1);
+      ptx::mbar_wait(full + 8 * ((cons + 1) % S), ((cons + 1) / S) & 1);
+      for (int j = 0; j < nrows; ++j) {
+        const uint32_t l2 = cons + j + 2;
+        ptx::mbar_wait(full + 8 * (l2 % S), (l2 / S) & 1);
+        const uint32_t stage = acc % AS;
+        ptx::mbar_wait(tempty + 8 * stage, ((acc / AS) & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + stage * 64;
+        // the descriptor's address field counts 16-byte units: slot = 1088, pixel = 8, 16 channels = 2, tap = 512
+        const uint64_t arow0 = adesc0 + static_cast<uint64_t>(((cons + j) % S) * (kSlotBytes >> 4));
+        const uint64_t arow1 = adesc0 + static_cast<uint64_t>(((cons + j + 1) % S) * (kSlotBytes >> 4));
+        const uint64_t arow2 = adesc0 + static_cast<uint64_t>(((cons + j + 2) % S) * (kSlotBytes >> 4));
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
-            // the descriptor's address field counts 16-byte units: slot = 1088, pixel = 8, 16 channels = 2, tap = 512
-            const uint64_t arow = adesc0 + static_cast<uint64_t>(((cons + j + dy) % S) * (kSlotBytes >> 4));
+            const uint64_t arow = dy == 0 ? arow0 : (dy == 1 ? arow1 : arow2);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
@@ -178,22 +185,27 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
           }
           ptx::mma_commit(tfull + 8 * stage);               // accumulator ready for the epilogue
           ptx::mma_commit(empty + 8 * ((cons + j) % S));    // input row y-1 is no longer needed
-          ++acc;
         }
+        __syncwarp();
+        ++acc;
+      }
+      if (ptx::elect_one()) {
         ptx::mma_commit(empty + 8 * ((cons + nrows) % S));
         ptx::mma_commit(empty + 8 * ((cons + nrows + 1) % S));
-        cons += nrows + 2;
       }
-      // drain: commits complete in order, so once this one lands no arrive is still in flight
-      ptx::mma_commit(wbar);
-      ptx::mbar_wait(wbar, 1);
+      __syncwarp();
+      cons += nrows + 2;
     }
+    // drain: commits complete in order, so once this one lands no arrive is still in flight
+    if (ptx::elect_one()) ptx::mma_commit(wbar);
+    __syncwarp();
+    ptx::mbar_wait(wbar, 1);
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int lgrp = warp & 3;                       // TMEM lanes this warp may read: 32*lgrp .. +31
     const int half = (warp - 2) >> 2;                // which 32 of the 64 channels
     const int L = lgrp * 32 + lane;                  // pixel within the strip == staging row
-    const bool leader = (tid == 64);
+    const bool lead_warp = (warp == 2);               // its elected lane issues the TMA stores / residual loads
     const bool has_skip = p.epi == EPI_SCALE_SKIP;
     uint8_t* my_row = stg_ptr + L * 128;
     const int sw = L & 7;
@@ -202,11 +214,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     for (int j = 0; j < 32; ++j) bias_r[j] = p.epi == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
 
     uint32_t acc = 0;                                // output-row counter over ALL items
-    if (has_skip && leader && blockIdx.x < p.items) { // residual tile of the very first row
+    if (has_skip && lead_warp && blockIdx.x < p.items) { // residual tile of the very first row
       int n, x0, y0, y1;
       conv_decode_item(p, blockIdx.x, ncg, n, x0, y0, y1);
-      ptx::mbar_expect_tx(skfull, kStageBytes);
-      ptx::tma_load_4d(stg, &maps.skip, skfull, 0, x0, y0, n);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(skfull, kStageBytes);
+        ptx::tma_load_4d(stg, &maps.skip, skfull, 0, x0, y0, n);
+      }
+      __syncwarp();
     }
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int n, x0, y0, y1;
@@ -219,7 +234,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
         if (has_skip) {
           ptx::mbar_wait(skfull + 8 * os, (acc / OS) & 1);
         } else {
-          if (leader) ptx::bulk_wait_read<OS - 1>();
+          if (lead_warp) {
+            if (ptx::elect_one()) ptx::bulk_wait_read<OS - 1>();
+            __syncwarp();
+          }
           ptx::named_bar_sync(1, kEpiThreads);
         }
         // (2) accumulator -> registers, TMEM stage back to the MMA warp
@@ -257,18 +275,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
         // (4) hand the tile to the async proxy and store it
         ptx::fence_proxy_async_smem();
         ptx::named_bar_sync(2, kEpiThreads);
-        if (leader) {
-          ptx::tma_store_4d(omap, stg + os * kStageBytes, 0, x0, y, n);
-          ptx::bulk_commit();
-          if (has_skip) {
-            // residual tile of the NEXT row goes into the other staging tile once that tile's store has read it
-            int nn = n, nx0 = x0, ny = y + 1;
-            bool more = true;
-            if (ny >= y1) {
-              const int nitem = item + gridDim.x;
-              more = nitem < p.items;
-              if (more) { int t1; conv_decode_item(p, nitem, ncg, nn, nx0, ny, t1); }
-            }
+        if (lead_warp) {
+          // residual tile of the NEXT row goes into the other staging tile once that tile's store has read it
+          int nn = n, nx0 = x0, ny = y + 1;
+          bool more = has_skip;
+          if (has_skip && ny >= y1) {
+            const int nitem = item + gridDim.x;
+            more = nitem < p.items;
+            if (more) { int t1; conv_decode_item(p, nitem, ncg, nn, nx0, ny, t1); }
+          }
+          if (ptx::elect_one()) {
+            ptx::tma_store_4d(omap, stg + os * kStageBytes, 0, x0, y, n);
+            ptx::bulk_commit();
             if (more) {
               const uint32_t nos = (acc + 1) % OS;
               ptx::bulk_wait_read<OS - 1>();            // every store but the one just issued has read its tile
@@ -276,10 +294,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
               ptx::tma_load_4d(stg + nos * kStageBytes, &maps.skip, skfull + 8 * nos, 0, nx0, ny, nn);
             }
           }
+          __syncwarp();
         }
       }
     }
-    if (leader) ptx::bulk_wait<0>();                     // all stores complete before the CTA exits
+    if (lead_warp) {
+      if (ptx::elect_one()) ptx::bulk_wait<0>();          // all stores complete before the CTA exits
+      __syncwarp();
+    }
   }
   __syncwarp();
   ptx::tc_fence_before_sync();

@@ -80,39 +80,44 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
   const uint32_t tmem_base = *tslot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: whole warp converged, one elected lane issues (keeps TMA operands in uniform registers)
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, 4096);
       ptx::bulk_load_1d(wsm, p.w_img, 4096, wbar);
-      uint32_t ld = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int n, xl, y0, y1;
-        head_decode_item(p, item, n, xl, y0, y1);
-        for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
-          const uint32_t slot = ld % S;
-          ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
+    }
+    __syncwarp();
+    uint32_t ld = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, xl, y0, y1;
+      head_decode_item(p, item, n, xl, y0, y1);
+      for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
+        const uint32_t slot = ld % S;
+        ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_expect_tx(full + 8 * slot, kHeadSlotBytes);
           ptx::tma_load_4d(ring + slot * kHeadSlotBytes, &maps.u, full + 8 * slot, 0, xl, yy, n);
           ptx::tma_load_4d(ring + slot * kHeadSlotBytes + kStageBytes, &maps.r, full + 8 * slot, 0, xl, yy, n);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_f16_f32(128, 16);
-      const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
-      const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
-      ptx::mbar_wait(wbar, 0);
-      ptx::tc_fence_after_sync();
-      uint32_t ld = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int n, xl, y0, y1;
-        head_decode_item(p, item, n, xl, y0, y1);
-        for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
-          const uint32_t slot = ld % S, stage = ld % AS;
-          ptx::mbar_wait(full + 8 * slot, (ld / S) & 1);
-          ptx::mbar_wait(tempty + 8 * stage, ((ld / AS) & 1) ^ 1);
-          ptx::tc_fence_after_sync();
-          const uint64_t arow = adesc0 + static_cast<uint64_t>(slot * (kHeadSlotBytes >> 4));
+    constexpr uint32_t idesc = ptx::idesc_f16_f32(128, 16);
+    const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
+    const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
+    ptx::mbar_wait(wbar, 0);
+    ptx::tc_fence_after_sync();
+    uint32_t ld = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, xl, y0, y1;
+      head_decode_item(p, item, n, xl, y0, y1);
+      for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
+        const uint32_t slot = ld % S, stage = ld % AS;
+        ptx::mbar_wait(full + 8 * slot, (ld / S) & 1);
+        ptx::mbar_wait(tempty + 8 * stage, ((ld / AS) & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint64_t arow = adesc0 + static_cast<uint64_t>(slot * (kHeadSlotBytes >> 4));
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int b = 0; b < 2; ++b)
 #pragma unroll
@@ -121,10 +126,12 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
           ptx::mma_commit(tfull + 8 * stage);
           ptx::mma_commit(empty + 8 * slot);
         }
+        __syncwarp();
       }
-      ptx::mma_commit(wbar);
-      ptx::mbar_wait(wbar, 1);
     }
+    if (ptx::elect_one()) ptx::mma_commit(wbar);
+    __syncwarp();
+    ptx::mbar_wait(wbar, 1);
   } else {
     const int lgrp = warp & 3;
     const int L = lgrp * 32 + lane;                 // loaded pixel index 0..127

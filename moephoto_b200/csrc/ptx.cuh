@@ -11,6 +11,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// one lane of a CONVERGED warp (deterministic for a given mask).  Issuing TMA / tcgen05 under this predicate
+// keeps their operands in uniform registers; under `lane == 0` the compiler wraps every such instruction in
+// an ELECT/BRA.U.ANY loop (measured: ~84 issue cycles per tcgen05.mma, profiles/r01_conv_ncu_issue_bound.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -271,3 +271,40 @@ def test_errors_are_status_codes_not_crashes(engine):
     cfgopt = _sr_opt('a2', 2, ram=1000)
     IP.doCrop(cfgopt, x)
   config.freeMemOverride = None
+
+
+def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
+  """BASELINE configs[3] in miniature: two 16-bit frames (bgr48le as video.py pipes them) -> toTorch(16) ->
+  DN lite15 -> SR a2 -> toOutput(16), frames batched as planes (bit-identical to per-frame calls
+  when cropsize is pinned), checked against the oracle with the engine's rounding points."""
+  from oracle import net as N, tiling as T
+  from moephoto_b200 import runSR, runDN, imageProcess as IP
+  from moephoto_b200.config import config
+  rng = np.random.default_rng(21)
+  base = (np.clip(np.add.outer(np.linspace(0.1, 0.8, 40), np.linspace(0.0, 0.2, 56)), 0, 1) * 65535)
+  frames = [np.clip(base[:, :, None] + rng.normal(0, 900, (40, 56, 3)), 0, 65535).astype(np.uint16) for _ in range(2)]
+  config.freeMemOverride, config.crop_dn, config.crop_sr = int(4e9), 32, 32
+  try:
+    odn = runDN.getOpt({'model': 'lite15'}, weights=H.load_weights('dn_lite15'))
+    osr = runSR.getOpt({'model': 'a', 'scale': 2}, weights=H.load_weights('a2'))
+    x = torch.cat([IP.toTorch(16, swapRB=True)(f) for f in frames], 0)           # (6,40,56): BGR->RGB on load
+    y = runSR.sr(osr)(IP.RGBFilter(odn)(x))
+    assert tuple(y.shape) == (6, 80, 112)
+    out = [IP.toOutput(16, swapRB=True)(y[3 * i:3 * i + 3]) for i in range(2)]
+    # per-frame calls give the same bits as the batch
+    y0 = runSR.sr(runSR.getOpt({'model': 'a', 'scale': 2}, weights=H.load_weights('a2')))(
+        IP.RGBFilter(runDN.getOpt({'model': 'lite15'}, weights=H.load_weights('dn_lite15')))(x[:3]))
+    assert torch.equal(y0, y[:3])
+    # oracle chain
+    sdn, ssr = H.load_weights('dn_lite15'), H.load_weights('a2')
+    for i, f in enumerate(frames):
+      xi = T.to_planar(f[:, :, ::-1], 16, np.float16).astype(np.float32)
+      pd = T.make_plan((3, 40, 56), 4e9, .95 / 1253.4, 7, 1, 8, 32)
+      d = T.rgb_filter(lambda a: N.forward(sdn, a, mode='f16io'), xi, pd, 1.0, np.float16).astype(np.float32)
+      ps = T.make_plan((3, 40, 56), 4e9, .9 / 2473., 5, 2, 8, 32)
+      s = T.do_crop(lambda a: N.forward(ssr, a, mode='f16io'), d, ps, np.float16)
+      assert np.abs(y[3 * i:3 * i + 3].float().cpu().numpy() - s.astype(np.float32)).max() <= 2e-3
+      want = T.to_output(s.astype(np.float32), 16)[:, :, ::-1]
+      assert np.abs(out[i].astype(np.int64) - (want.astype(np.int64) & 0xFFFF)).max() <= 140        # 2e-3 * 65536
+  finally:
+    config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
