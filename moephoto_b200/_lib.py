@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libmoephoto_b200.so')
 SOURCES = [os.path.join(HERE, 'csrc', 'engine.cu')]
-HEADERS = [os.path.join(HERE, 'csrc', n) for n in ('ptx.cuh', 'conv_tc.cuh', 'kernels_simt.cuh', 'blob.h')] + \
+HEADERS = [os.path.join(HERE, 'csrc', n) for n in sorted(os.listdir(os.path.join(HERE, 'csrc'))) if n.endswith(('.cuh', '.h'))] + \
           [os.path.join(HERE, '..', 'include', 'moephoto_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']

@@ -1,0 +1,247 @@
+// The upsample convolutions (64 -> 256, PixelShuffle(2), +bias, PReLU: models.py:29-33) hold 68 % of a4's
+// FLOPs, and a 128x64x16 tcgen05.mma cannot run at full rate: its 6 KB of shared-memory operands take 48.5
+// cycles to fetch where the math takes 32 (profiles/r01_mma_rate_microbench.log).  This kernel gives those
+// layers an N = 128 tile with the SAME shared-memory footprint per SM by pairing two CTAs (cta_group::2):
+//   * the pair covers 256 pixels of an output row: CTA0 the 128-px strip 2s, CTA1 the strip 2s+1 (M = 256);
+//   * each CTA keeps ONE 64-channel weight chunk (73.7 KB); the MMA reads B rows 0..63 from CTA0 and 64..127
+//     from CTA1, so every input row is multiplied by two sub-pixel chunks per instruction: per MMA each SM
+//     fetches 4 KB (A) + 2 KB (its half of B) for 64 cycles of math instead of 32;
+//   * accumulators: 128 lanes x 128 columns per CTA and stage, 4 stages = all 512 TMEM columns;
+//   * everything else is conv_tc.cuh: 130-px TMA row ring, nine shifted descriptor views, TMA-store
+//     epilogue (two staging tiles = the two chunks of one row).
+// Protocol across the pair: the leader (cluster rank 0) issues every MMA.  `full` and `tempty` barriers live
+// in the leader (both CTAs' TMA loads complete_tx there; all 512 epilogue threads arrive there); `empty`
+// and `tfull` exist in both CTAs and are signalled by multicast tcgen05.commit.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace moe {
+
+struct PairCfg {
+  static constexpr int kSlots = 6;
+  static constexpr int kAccStages = 4;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kChunkImgBytes + 2 * kStageBytes + 1024;
+};
+
+// item -> (chunk group g, plane n, strip pair sp, rows)
+__device__ __forceinline__ void pair_decode_item(const ConvParams& p, int item, int& g, int& n, int& sp, int& y0, int& y1) {
+  g = item & 1;
+  int rest = item >> 1;
+  const int seg = rest % p.nseg;
+  rest /= p.nseg;
+  sp = rest % p.strips;          // p.strips holds the number of strip PAIRS here
+  n = rest / p.strips;
+  y0 = seg * p.seg_rows;
+  y1 = min(p.H, y0 + p.seg_rows);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
+{
+  using Cfg = PairCfg;
+  constexpr int S = Cfg::kSlots, AS = Cfg::kAccStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t ring = base;
+  const uint32_t wsm = ring + S * kSlotBytes;
+  const uint32_t stg = wsm + kChunkImgBytes;                       // two staging tiles (one per chunk), 1024-aligned
+  const uint32_t bars = stg + 2 * kStageBytes;
+  const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
+  const uint32_t wbar = tempty + 8 * AS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
+  const uint32_t bias_sm = bars + 256;                              // 128 floats, 16-byte aligned for float4 reads
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
+  uint8_t* stg_ptr = smem + (stg - base);
+  float* bias_ptr = reinterpret_cast<float*>(smem + (bias_sm - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader_cta = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int g_fixed = pair & 1;                   // npairs is even (host), so a pair keeps its chunk group
+  const int my_chunk = g_fixed * 2 + static_cast<int>(rank);
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
+    for (int i = 0; i < AS; ++i) { ptx::mbar_init(tfull + 8 * i, 1); ptx::mbar_init(tempty + 8 * i, 2 * kEpiThreads); }
+    ptx::mbar_init(wbar, 1);
+    ptx::mbar_init(wpeer, 1);
+    ptx::mbar_init(dbar, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&maps.in);
+  }
+  for (int i = tid; i < 128; i += kConvThreads) bias_ptr[i] = p.bias[g_fixed * 128 + i];
+  if (warp == 1) ptx::tmem_alloc_pair(tslot, Cfg::kTmemCols);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();                        // the peer's barriers are initialised before any remote arrive
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tslot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (each CTA loads its own strip)
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(wbar, kChunkImgBytes);
+      const uint8_t* src = p.w_img + static_cast<size_t>(my_chunk) * kChunkImgBytes;
+      for (int tap = 0; tap < 9; ++tap) ptx::bulk_load_1d(wsm + tap * 8192, src + tap * 8192, 8192, wbar);
+    }
+    __syncwarp();
+    uint32_t ld = 0;
+    for (int item = pair; item < p.items; item += npairs) {
+      int g, n, sp, y0, y1;
+      pair_decode_item(p, item, g, n, sp, y0, y1);
+      const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
+        const uint32_t slot = ld % S;
+        ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
+        if (ptx::elect_one()) {
+          if (leader_cta) ptx::mbar_expect_tx(full + 8 * slot, 2 * kRowBytes);     // both CTAs' rows
+          ptx::tma_load_4d_pair(ring + slot * kSlotBytes, &maps.in, ptx::mapa(full + 8 * slot, 0), 0, x0 - 1, yy, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (!leader_cta) {
+      // ---------------------------------------------------------- peer: report "my weights are in smem" to the leader
+      ptx::mbar_wait(wbar, 0);
+      if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(wpeer, 0));
+      __syncwarp();
+    } else {
+      // ---------------------------------------------------------- leader: MMA issuer for the pair
+      constexpr uint32_t idesc = ptx::idesc_f16_f32(256, 128);
+      const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
+      const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
+      ptx::mbar_wait(wbar, 0);
+      ptx::mbar_wait(wpeer, 0);
+      ptx::tc_fence_after_sync();
+      uint32_t cons = 0, acc = 0;
+      for (int item = pair; item < p.items; item += npairs) {
+        int g, n, sp, y0, y1;
+        pair_decode_item(p, item, g, n, sp, y0, y1);
+        const int nrows = y1 - y0;
+        ptx::mbar_wait(full + 8 * (cons % S), (cons / S) & 1);
+        ptx::mbar_wait(full + 8 * ((cons + 1) % S), ((cons + 1) / S) & 1);
+        for (int j = 0; j < nrows; ++j) {
+          const uint32_t l2 = cons + j + 2;
+          ptx::mbar_wait(full + 8 * (l2 % S), (l2 / S) & 1);
+          const uint32_t stage = acc % AS;
+          ptx::mbar_wait(tempty + 8 * stage, ((acc / AS) & 1) ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + stage * 128;
+          const uint64_t arow0 = adesc0 + static_cast<uint64_t>(((cons + j) % S) * (kSlotBytes >> 4));
+          const uint64_t arow1 = adesc0 + static_cast<uint64_t>(((cons + j + 1) % S) * (kSlotBytes >> 4));
+          const uint64_t arow2 = adesc0 + static_cast<uint64_t>(((cons + j + 2) % S) * (kSlotBytes >> 4));
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint64_t arow = dy == 0 ? arow0 : (dy == 1 ? arow1 : arow2);
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, (dy | dx | k) != 0);
+                }
+              }
+            }
+            ptx::mma_commit_pair_mc(tfull + 8 * stage, 3);              // both CTAs' epilogues
+            ptx::mma_commit_pair_mc(empty + 8 * ((cons + j) % S), 3);   // both CTAs' producers
+          }
+          __syncwarp();
+          ++acc;
+        }
+        if (ptx::elect_one()) {
+          ptx::mma_commit_pair_mc(empty + 8 * ((cons + nrows) % S), 3);
+          ptx::mma_commit_pair_mc(empty + 8 * ((cons + nrows + 1) % S), 3);
+        }
+        __syncwarp();
+        cons += nrows + 2;
+      }
+      if (ptx::elect_one()) ptx::mma_commit_pair(dbar);     // drain
+      __syncwarp();
+      ptx::mbar_wait(dbar, 0);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+    const int lgrp = warp & 3;                       // TMEM lanes 32*lgrp .. +31
+    const int ch = (warp - 2) >> 2;                  // which of the pair's two chunks (64 accumulator columns)
+    const int L = lgrp * 32 + lane;                  // pixel within this CTA's strip == staging row
+    const bool lead_warp = (warp == 2);
+    uint8_t* my_row = stg_ptr + ch * kStageBytes + L * 128;
+    const int sw = L & 7;
+    const uint32_t tempty_leader = ptx::mapa(tempty, 0);
+    const float* my_bias = bias_ptr + ch * 64;
+    const CUtensorMap* omap0 = &maps.out[g_fixed * 2];
+    const CUtensorMap* omap1 = &maps.out[g_fixed * 2 + 1];
+    uint32_t acc = 0;
+    for (int item = pair; item < p.items; item += npairs) {
+      int g, n, sp, y0, y1;
+      pair_decode_item(p, item, g, n, sp, y0, y1);
+      const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      for (int y = y0; y < y1; ++y, ++acc) {
+        const uint32_t stage = acc % AS;
+        ptx::mbar_wait(tfull + 8 * stage, (acc / AS) & 1);
+        ptx::tc_fence_after_sync();
+        uint4 pk[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 128 + ch * 64 + h * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = q * 8 + e * 2;
+              const float f0 = epi_apply(__uint_as_float(v[j]), EPI_BIAS_PRELU, p.param, bb[e * 2], 0.f);
+              const float f1 = epi_apply(__uint_as_float(v[j + 1]), EPI_BIAS_PRELU, p.param, bb[e * 2 + 1], 0.f);
+              const __half2 hv = __floats2half2_rn(f0, f1);
+              w[e] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            pk[h * 4 + q] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive_cluster(tempty_leader + 8 * stage);     // this thread is done with the TMEM stage
+        // the staging tiles are single-buffered: the previous row's stores must have read them
+        if (lead_warp) {
+          if (ptx::elect_one()) ptx::bulk_wait_read<0>();
+          __syncwarp();
+        }
+        ptx::named_bar_sync(1, kEpiThreads);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = pk[c];
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(2, kEpiThreads);
+        if (lead_warp) {
+          if (ptx::elect_one()) {
+            ptx::tma_store_4d(omap0, stg, 0, x0, y, n);
+            ptx::tma_store_4d(omap1, stg + kStageBytes, 0, x0, y, n);
+            ptx::bulk_commit();
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lead_warp) {
+      if (ptx::elect_one()) ptx::bulk_wait<0>();
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();                          // nobody frees TMEM / exits while the peer may still use it
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace moe

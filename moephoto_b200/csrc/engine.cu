@@ -16,6 +16,7 @@
 #include "../../include/moephoto_b200.h"
 #include "blob.h"
 #include "conv_tc.cuh"
+#include "conv_pair.cuh"
 #include "kernels_simt.cuh"
 #include "head_tc.cuh"
 
@@ -59,7 +60,8 @@ struct MoeEngine {
   std::atomic<int64_t> launches{0};
   int simt = 0;
   int cur_feat = 64;       // real filter count of the model being run (48 for NetDN) — FLOP accounting only
-  bool smem_attr_set = false, head_attr_set = false;
+  bool smem_attr_set = false, head_attr_set = false, pair_attr_set = false;
+  int no_pair = 0;         // 1 = keep the upsample convs on the single-CTA kernel (A/B switch)
   // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3, 2 heads, 3 frame I/O
   bool profiling = false;
   struct Span { int cls; cudaEvent_t a, b; double work; };
@@ -139,18 +141,36 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
     conv3x3_simt_kernel<<<grid_for(threads, 256, e->sm_count), 256, 0, st>>>(p);
     return check_launch(e, "conv3x3_simt_kernel");
   }
+  const bool pair_path = r == 2 && epi == EPI_BIAS_PRELU && !e->no_pair && e->sm_count >= 4;
+  if (pair_path) {
+    // CTA pairs (cta_group::2): 256 px x 128 channels per MMA, conv_pair.cuh
+    const int npairs = (e->sm_count / 2) & ~1;              // even, so a pair keeps its chunk group (weights stay resident)
+    const int strips1 = (W + kStripW - 1) / kStripW;
+    p.strips = (strips1 + 1) / 2;                            // strip PAIRS
+    const int64_t base_items = 2ll * N * p.strips;
+    int nseg = static_cast<int>((4ll * npairs + base_items - 1) / base_items);
+    nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
+    p.seg_rows = (H + nseg - 1) / nseg;
+    p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+    const int64_t items = base_items * p.nseg;
+    if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
+    p.items = static_cast<int>(items);
+  }
   const int ncg = r * r;                                    // one 64-channel chunk per CTA
   const int G = std::max(ncg, e->sm_count / ncg * ncg);    // CTAs; multiple of ncg so a CTA keeps its chunk
-  p.strips = (W + kStripW - 1) / kStripW;
-  const int64_t base_items = static_cast<int64_t>(N) * p.strips * ncg;
-  int nseg = static_cast<int>((4ll * G + base_items - 1) / base_items);
-  nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
-  p.seg_rows = (H + nseg - 1) / nseg;
-  p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
-  const int64_t items = base_items * p.nseg;
-  if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
-  p.items = static_cast<int>(items);
-  const int grid = static_cast<int>(std::min<int64_t>(G, items));   // items is a multiple of ncg
+  int grid = 0;
+  if (!pair_path) {
+    p.strips = (W + kStripW - 1) / kStripW;
+    const int64_t base_items = static_cast<int64_t>(N) * p.strips * ncg;
+    int nseg = static_cast<int>((4ll * G + base_items - 1) / base_items);
+    nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
+    p.seg_rows = (H + nseg - 1) / nseg;
+    p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+    const int64_t items = base_items * p.nseg;
+    if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
+    p.items = static_cast<int>(items);
+    grid = static_cast<int>(std::min<int64_t>(G, items));   // items is a multiple of ncg
+  }
 
   // tensor maps: input rows (130-px box), residual rows and one output view per PixelShuffle sub-pixel
   ConvMaps maps;
@@ -174,6 +194,15 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
                 static_cast<cuuint64_t>(r) * Wo * 128, Ho * Wo * 128, kStripW);
   }
   if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d H=%d W=%d r=%d", (int)cr, N, H, W, r);
+  if (pair_path) {
+    if (!e->pair_attr_set) {
+      MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+      e->pair_attr_set = true;
+    }
+    const int npairs = std::min<int64_t>((e->sm_count / 2) & ~1, (p.items + 1) / 2 * 2);
+    conv3x3_pair_kernel<<<2 * npairs, kConvThreads, PairCfg::kSmemBytes, st>>>(maps, p);
+    return check_launch(e, "conv3x3_pair_kernel");
+  }
   if (!e->smem_attr_set) {
     MOE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg::kSmemBytes));
     e->smem_attr_set = true;
@@ -361,6 +390,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
 {
   if (!e) return fail(MOE_ERR_INVALID, "engine is null");
   e->simt = simt & 1;
+  e->no_pair = (simt >> 1) & 1;
   return MOE_OK;
 }
 

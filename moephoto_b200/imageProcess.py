@@ -60,8 +60,8 @@ class Engine:
     _lib.check(self.lib.moe_engine_profile_read(self.handle, ms, work, n))
     return {k: (ms[i], work[i], n[i]) for i, k in enumerate(('conv_input', 'conv3x3', 'head', 'other'))}
 
-  def set_conv_path(self, simt=False):
-    _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt))))
+  def set_conv_path(self, simt=False, no_pair=False):
+    _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(no_pair)) << 1)))
 
   def get_workspace(self, nbytes):
     if self.workspace is None or self.workspace.numel() < nbytes:

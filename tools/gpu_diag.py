@@ -118,8 +118,10 @@ def golden_suite(eng):
 def timing(eng):
   sys.path.insert(0, os.path.join(ROOT, 'tests'))
   import helpers as Hh
-  for key, scale, shape in (('a2', 2, (3, 1080, 1920)), ('a4', 4, (3, 2160, 3840))):
+  for key, scale, shape, no_pair in (('a2', 2, (3, 1080, 1920), False), ('a4', 4, (3, 2160, 3840), True), ('a4', 4, (3, 2160, 3840), False)):
     try:
+      eng.set_conv_path(simt=False, no_pair=no_pair)
+      say('[time] upsample convs on CTA pairs: %s' % (not no_pair))
       sd = Hh.load_weights(key)
       opt = runSR.getOpt({'model': 'a', 'scale': scale}, weights=sd)
       x = torch.rand(shape, device='cuda').half()
