@@ -317,13 +317,15 @@ def main():
             'd2h_bytes_per_step': H_IN * SCALE * W_IN * SCALE * 3, 'path': 'moe_enhance_host (C ABI, pinned host uint8 in/out)' if world == 1 else
             'toTorch -> sharded doCrop (NCCL) -> moe_to_output -> pinned host'},
     'gpu_launches': launches,
-    'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel (all %d launches of rank 0 in the timed region)' % conv_n,
+    'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel + conv3x3_pair_kernel (all %d 3x3-convolution launches of rank 0 in the timed region)' % conv_n,
                  'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'peak_source': pk['src'],
                  'traffic': traffic, 'avg_launch_ms': conv_ms / max(1, conv_n),
                  'algorithmic_flops_per_launch': conv_flops / max(1, conv_n),
                  'share_of_step': conv_ms / total_ms,
                  'other_kernels': {k: {'ms_per_step': v[0] / args.steps, 'GBps': (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0), 'launches': v[2]}
-                                   for k, v in prof.items() if k in ('conv_input', 'head')}},
+                                   for k, v in prof.items() if k in ('conv_input', 'head')},
+                 'conv_breakdown': {k: {'ms_per_step': v[0] / args.steps, 'TFLOPs': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), 'launches': v[2]}
+                                    for k, v in prof.items() if k in ('conv_trunk', 'conv_up')}},
     'whole_step_tflops': FLOP_PER_LR_PIXEL_PLANE * 3.0 * H_IN * W_IN / (ms_step * 1e-3) / 1e12,
   }
   if world == 1 and not args.no_cpu_baseline:

@@ -87,8 +87,8 @@ void moe_engine_destroy(MoeEngine* e);
 /* number of this library's kernels launched since the engine was created (bench.py "gpu_launches") */
 int64_t moe_engine_launch_count(const MoeEngine* e);
 /* Per-launch device timing for roofline reports: while enabled, every kernel launch is bracketed by
- * a CUDA event pair on its stream.  _read waits for them, returns per class (0 conv_input, 1 conv3x3,
- * 2 heads+blend, 3 unused) the summed milliseconds, the summed algorithmic work (FLOPs for class 1,
+ * a CUDA event pair on its stream.  _read waits for them, returns per class (0 conv_input, 1 conv3x3 with
+ * r = 1, 2 heads+blend, 3 upsample conv3x3 with PixelShuffle) the summed milliseconds, the summed algorithmic work (FLOPs for classes 1 and 3,
  * bytes otherwise) and the launch count, and resets the counters. */
 int moe_engine_profile(MoeEngine* e, int enable);
 int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t launches[4]);

@@ -10,7 +10,7 @@
 //   * everything else is conv_tc.cuh: 130-px TMA row ring, nine shifted descriptor views, TMA-store
 //     epilogue (two staging tiles = the two chunks of one row).
 // Protocol across the pair: the leader (cluster rank 0) issues every MMA.  `full` and `tempty` barriers live
-// in the leader (both CTAs' TMA loads complete_tx there; all 512 epilogue threads arrive there); `empty`
+// in the leader (both CTAs' TMA loads complete_tx there; the 16 epilogue warps arrive there); `empty`
 // and `tfull` exist in both CTAs and are signalled by multicast tcgen05.commit.
 #pragma once
 #include "conv_tc.cuh"
@@ -65,7 +65,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
-    for (int i = 0; i < AS; ++i) { ptx::mbar_init(tfull + 8 * i, 1); ptx::mbar_init(tempty + 8 * i, 2 * kEpiThreads); }
+    for (int i = 0; i < AS; ++i) { ptx::mbar_init(tfull + 8 * i, 1); ptx::mbar_init(tempty + 8 * i, 2 * kEpiWarps); }
     ptx::mbar_init(wbar, 1);
     ptx::mbar_init(wpeer, 1);
     ptx::mbar_init(dbar, 1);
@@ -208,7 +208,8 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
           }
         }
         ptx::tc_fence_before_sync();
-        ptx::mbar_arrive_cluster(tempty_leader + 8 * stage);     // this thread is done with the TMEM stage
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + 8 * stage);   // this warp is done with the TMEM stage
         // the staging tiles are single-buffered: the previous row's stores must have read them
         if (lead_warp) {
           if (ptx::elect_one()) ptx::bulk_wait_read<0>();

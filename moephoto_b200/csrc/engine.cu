@@ -62,7 +62,7 @@ struct MoeEngine {
   int cur_feat = 64;       // real filter count of the model being run (48 for NetDN) — FLOP accounting only
   bool smem_attr_set = false, head_attr_set = false, pair_attr_set = false;
   int no_pair = 0;         // 1 = keep the upsample convs on the single-CTA kernel (A/B switch)
-  // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3, 2 heads, 3 frame I/O
+  // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3 r=1, 2 heads, 3 upsample conv3x3
   bool profiling = false;
   struct Span { int cls; cudaEvent_t a, b; double work; };
   std::vector<Span> spans;
@@ -135,7 +135,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
   p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param;
   // algorithmic FLOPs: 2 * 9 taps * Cin * Cout per input pixel (padded channels are not counted)
-  Timed timed(e, st, 1, 2.0 * 9 * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
+  Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * 9 * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
   if (e->simt) {
     const int64_t threads = static_cast<int64_t>(N) * H * W * r * r * 8;
     conv3x3_simt_kernel<<<grid_for(threads, 256, e->sm_count), 256, 0, st>>>(p);
@@ -517,7 +517,7 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     e->cur_feat = m->feat;
     {
     Timed timed(e, st, 0, static_cast<double>(N) * H * W * (2 + 128));     // bytes: read 1 fp16, write 64 fp16
-    conv_first_kernel<<<grid_for(static_cast<int64_t>(N) * H * W * 8, 256, e->sm_count), 256, 0, st>>>(fp);
+    conv_first_kernel<<<grid_for(static_cast<int64_t>(N) * H * ((W + 3) / 4) * 8, 256, e->sm_count), 256, 0, st>>>(fp);
     }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 

@@ -29,48 +29,66 @@ struct FirstParams {
   __half* out;                     // NHWC (N,H,W,64)
 };
 
-// conv_input (1 -> 64, 3x3) + PReLU  (models.py:112,118).  8 threads per pixel, 8 channels each.
+// conv_input (1 -> 64, 3x3) + PReLU  (models.py:112,118).  A thread computes 8 output channels of 4
+// consecutive pixels from one 3x6 input window (8 threads = one 4-pixel group, so every store instruction of
+// a warp writes four full 128-byte pixels); bandwidth-bound: 2 B read, 128 B written per pixel.
 __global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p)
 {
   __shared__ float ws[9 * 64];
   for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) ws[i] = p.w[i];
   __syncthreads();
-  const int64_t total = static_cast<int64_t>(p.N) * p.H * p.W * 8;
+  const int gw = (p.W + 3) >> 2;                                   // 4-pixel groups per row
+  const int64_t total = static_cast<int64_t>(p.N) * p.H * gw * 8;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(idx & 7);
-    const int64_t pix = idx >> 3;
-    const int x = static_cast<int>(pix % p.W);
-    const int y = static_cast<int>((pix / p.W) % p.H);
-    const int n = static_cast<int>(pix / (static_cast<int64_t>(p.W) * p.H));
-    float a[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = 0.f;
+    const int64_t grp = idx >> 3;
+    const int x = static_cast<int>(grp % gw) * 4;
+    const int y = static_cast<int>((grp / gw) % p.H);
+    const int n = static_cast<int>(grp / (static_cast<int64_t>(gw) * p.H));
+    float win[3][6];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int yy = y + dy - 1;
       const int sy = (yy < 0 || yy >= p.H) ? -1 : pad_src(p.top + yy, p.in_h, p.in_h + p.pad_h);
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
+      for (int dx = 0; dx < 6; ++dx) {
         const int xx = x + dx - 1;
         const int sx = (xx < 0 || xx >= p.W) ? -1 : pad_src(p.left + xx, p.in_w, p.in_w + p.pad_w);
-        float v = 0.f;
-        if (sy >= 0 && sx >= 0) v = __half2float(p.img[n * p.plane_stride + sy * p.row_stride + sx]);
-        const float* wr = ws + (dy * 3 + dx) * 64 + g * 8;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) a[c] = fmaf(v, wr[c], a[c]);
+        win[dy][dx] = (sy >= 0 && sx >= 0) ? __half2float(p.img[n * p.plane_stride + sy * p.row_stride + sx]) : 0.f;
       }
     }
-    uint32_t w[4];
+    float wreg[9][8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float f0 = a[2 * c], f1 = a[2 * c + 1];
-      f0 = f0 >= 0.f ? f0 : p.slope * f0;
-      f1 = f1 >= 0.f ? f1 : p.slope * f1;
-      const __half2 hv = __floats2half2_rn(f0, f1);
-      w[c] = *reinterpret_cast<const uint32_t*>(&hv);
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) wreg[t][c] = ws[t * 64 + g * 8 + c];
+    const size_t pix0 = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (x + i >= p.W) break;
+      float a[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float v = win[dy][i + dx];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[c] = fmaf(v, wreg[dy * 3 + dx][c], a[c]);
+        }
+      uint32_t w[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float f0 = a[2 * c], f1 = a[2 * c + 1];
+        f0 = f0 >= 0.f ? f0 : p.slope * f0;
+        f1 = f1 >= 0.f ? f1 : p.slope * f1;
+        const __half2 hv = __floats2half2_rn(f0, f1);
+        w[c] = *reinterpret_cast<const uint32_t*>(&hv);
+      }
+      reinterpret_cast<uint4*>(p.out + (pix0 + i) * 64)[g] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    reinterpret_cast<uint4*>(p.out + pix * 64)[g] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 

@@ -170,8 +170,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// plain (cta-scope release) arrive on a barrier that may live in the peer CTA.  NOT .release.cluster: that
+// form costs a MEMBAR.ALL.GPU + ERRBAR per call (25 % of the pair kernel's stall samples,
+// profiles/r01_pair_ncu.txt); the data handed over here is TMEM, ordered by tcgen05.fence, not global memory.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the completion bytes go to the mbarrier at `bar_cluster`
 // (a shared::cluster address, normally in the leader CTA)

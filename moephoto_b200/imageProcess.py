@@ -58,7 +58,9 @@ class Engine:
     """-> {class: (ms, work, launches)} for conv_input / conv3x3 / head, and resets the counters"""
     ms, work, n = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_int64 * 4)()
     _lib.check(self.lib.moe_engine_profile_read(self.handle, ms, work, n))
-    return {k: (ms[i], work[i], n[i]) for i, k in enumerate(('conv_input', 'conv3x3', 'head', 'other'))}
+    d = {k: (ms[i], work[i], n[i]) for i, k in enumerate(('conv_input', 'conv_trunk', 'head', 'conv_up'))}
+    d['conv3x3'] = tuple(a + b for a, b in zip(d['conv_trunk'], d['conv_up']))      # every 3x3 tensor-core convolution
+    return d
 
   def set_conv_path(self, simt=False, no_pair=False):
     _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(no_pair)) << 1)))

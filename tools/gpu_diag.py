@@ -136,7 +136,7 @@ def timing(eng):
       t1.record(); torch.cuda.synchronize()
       eng.profile(False)
       pr = eng.profile_read()
-      say('[prof] %s' % key, {k: '%.2f ms/frame, %d launches' % (v[0] / 3, v[2] // 3) for k, v in pr.items()},
+      say('[prof] %s' % key, {k: '%.2f ms/frame, %d launches, %.0f T(FLOP|B)/s' % (v[0] / 3, v[2] // 3, v[1] / max(v[0], 1e-9) / 1e9) for k, v in pr.items()},
           'conv TFLOP/s %.0f' % (pr['conv3x3'][1] / (pr['conv3x3'][0] * 1e-3) / 1e12), 'head GB/s %.0f' % (pr['head'][1] / (pr['head'][0] * 1e-3) / 1e9))
       ms = t0.elapsed_time(t1) / 3
       say('[time] %s %s tiles=%d  %.2f ms/frame  %.1f MPix/s out' % (key, shape, len(opt.plan.tiles), ms, y.shape[1] * y.shape[2] / ms / 1e3))
