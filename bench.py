@@ -213,6 +213,9 @@ def main():
   torch.cuda.set_device(local)
   config.deviceId = local
   if world > 1:
+    # the image exports NCCL_DEBUG=VERSION, which makes NCCL print its banner on STDOUT in front of the JSON line
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+      os.environ['NCCL_DEBUG'] = 'WARN'
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
   dev = torch.device('cuda', local)

@@ -245,4 +245,262 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same pairing for the 64 -> 64 trunk convolutions (conv_input2 and the twelve ARSB convs): M = 256,
+// N = 64, each CTA holding HALF of the output channels' weights (32 rows of every tap).  Per MMA an SM now
+// fetches 4 KB (A) + 1 KB (B half) instead of 4 + 2 KB: 40 instead of 48.5 cycles at the operand-fetch limit.
+// Epilogue exactly as in conv_tc.cuh (plain / PReLU / x scale + residual via TMA, double-buffered staging).
+struct PairTrunkCfg {
+  static constexpr int kSlots = 6;
+  static constexpr int kAccStages = 4;
+  static constexpr int kOutStages = 4;                           // staging tiles; the residual is prefetched 2 rows ahead
+  static constexpr int kSkipAhead = 2;
+  static constexpr uint32_t kWBytes = 9 * 32 * 128;              // this CTA's half of the weights
+  static constexpr uint32_t kTmemCols = kAccStages * 64;
+  static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kWBytes + kOutStages * kStageBytes + 1024;
+};
+
+// item -> (plane n, strip pair sp, rows); p.strips = number of strip pairs
+__device__ __forceinline__ void pair_trunk_decode(const ConvParams& p, int item, int& n, int& sp, int& y0, int& y1) {
+  const int seg = item % p.nseg;
+  int rest = item / p.nseg;
+  sp = rest % p.strips;
+  n = rest / p.strips;
+  y0 = seg * p.seg_rows;
+  y1 = min(p.H, y0 + p.seg_rows);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
+{
+  using Cfg = PairTrunkCfg;
+  constexpr int S = Cfg::kSlots, AS = Cfg::kAccStages, OS = Cfg::kOutStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t ring = base;
+  const uint32_t wsm = ring + S * kSlotBytes;
+  const uint32_t stg = wsm + Cfg::kWBytes;                          // 36 KB of weights keep this 1024-aligned
+  const uint32_t bars = stg + OS * kStageBytes;
+  const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
+  const uint32_t skfull = tempty + 8 * AS, wbar = skfull + 8 * OS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
+  uint8_t* stg_ptr = smem + (stg - base);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader_cta = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const CUtensorMap* omap = &maps.out[0];
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
+    for (int i = 0; i < AS; ++i) { ptx::mbar_init(tfull + 8 * i, 1); ptx::mbar_init(tempty + 8 * i, 2 * kEpiWarps); }
+    for (int i = 0; i < OS; ++i) ptx::mbar_init(skfull + 8 * i, 1);
+    ptx::mbar_init(wbar, 1);
+    ptx::mbar_init(wpeer, 1);
+    ptx::mbar_init(dbar, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&maps.in);
+    ptx::prefetch_tmap(omap);
+  }
+  if (warp == 1) ptx::tmem_alloc_pair(tslot, Cfg::kTmemCols);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tslot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(wbar, Cfg::kWBytes);
+      for (int tap = 0; tap < 9; ++tap)      // output channels 32*rank .. +31 of every tap
+        ptx::bulk_load_1d(wsm + tap * 4096, p.w_img + tap * 8192 + rank * 4096, 4096, wbar);
+    }
+    __syncwarp();
+    uint32_t ld = 0;
+    for (int item = pair; item < p.items; item += npairs) {
+      int n, sp, y0, y1;
+      pair_trunk_decode(p, item, n, sp, y0, y1);
+      const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
+        const uint32_t slot = ld % S;
+        ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
+        if (ptx::elect_one()) {
+          if (leader_cta) ptx::mbar_expect_tx(full + 8 * slot, 2 * kRowBytes);
+          ptx::tma_load_4d_pair(ring + slot * kSlotBytes, &maps.in, ptx::mapa(full + 8 * slot, 0), 0, x0 - 1, yy, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (!leader_cta) {
+      ptx::mbar_wait(wbar, 0);
+      if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(wpeer, 0));
+      __syncwarp();
+    } else {
+      constexpr uint32_t idesc = ptx::idesc_f16_f32(256, 64);
+      const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
+      const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
+      ptx::mbar_wait(wbar, 0);
+      ptx::mbar_wait(wpeer, 0);
+      ptx::tc_fence_after_sync();
+      uint32_t cons = 0, acc = 0;
+      for (int item = pair; item < p.items; item += npairs) {
+        int n, sp, y0, y1;
+        pair_trunk_decode(p, item, n, sp, y0, y1);
+        const int nrows = y1 - y0;
+        ptx::mbar_wait(full + 8 * (cons % S), (cons / S) & 1);
+        ptx::mbar_wait(full + 8 * ((cons + 1) % S), ((cons + 1) / S) & 1);
+        for (int j = 0; j < nrows; ++j) {
+          const uint32_t l2 = cons + j + 2;
+          ptx::mbar_wait(full + 8 * (l2 % S), (l2 / S) & 1);
+          const uint32_t stage = acc % AS;
+          ptx::mbar_wait(tempty + 8 * stage, ((acc / AS) & 1) ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + stage * 64;
+          const uint64_t arow0 = adesc0 + static_cast<uint64_t>(((cons + j) % S) * (kSlotBytes >> 4));
+          const uint64_t arow1 = adesc0 + static_cast<uint64_t>(((cons + j + 1) % S) * (kSlotBytes >> 4));
+          const uint64_t arow2 = adesc0 + static_cast<uint64_t>(((cons + j + 2) % S) * (kSlotBytes >> 4));
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint64_t arow = dy == 0 ? arow0 : (dy == 1 ? arow1 : arow2);
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 256 + k * 2), idesc, (dy | dx | k) != 0);
+                }
+              }
+            }
+            ptx::mma_commit_pair_mc(tfull + 8 * stage, 3);
+            ptx::mma_commit_pair_mc(empty + 8 * ((cons + j) % S), 3);
+          }
+          __syncwarp();
+          ++acc;
+        }
+        if (ptx::elect_one()) {
+          ptx::mma_commit_pair_mc(empty + 8 * ((cons + nrows) % S), 3);
+          ptx::mma_commit_pair_mc(empty + 8 * ((cons + nrows + 1) % S), 3);
+        }
+        __syncwarp();
+        cons += nrows + 2;
+      }
+      if (ptx::elect_one()) ptx::mma_commit_pair(dbar);
+      __syncwarp();
+      ptx::mbar_wait(dbar, 0);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (as conv_tc.cuh; tempty lives in the leader)
+    const int lgrp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int L = lgrp * 32 + lane;
+    const bool lead_warp = (warp == 2);
+    const bool has_skip = p.epi == EPI_SCALE_SKIP;
+    uint8_t* my_row = stg_ptr + L * 128;
+    const int sw = L & 7;
+    const uint32_t tempty_leader = ptx::mapa(tempty, 0);
+    uint32_t acc = 0;
+    // residual prefetch cursor: walks the same row sequence kSkipAhead rows ahead of the epilogue
+    int c_item = pair, c_n = 0, c_sp = 0, c_y = 0, c_y1 = 0;
+    uint32_t c_idx = 0;
+    bool c_ok = has_skip && lead_warp && c_item < p.items;
+    if (c_ok) pair_trunk_decode(p, c_item, c_n, c_sp, c_y, c_y1);
+    auto prefetch_skip = [&]() {            // lead warp, converged: issue the residual load of row c_idx and advance
+      if (!c_ok) return;
+      const uint32_t t = c_idx % OS;
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(skfull + 8 * t, kStageBytes);
+        ptx::tma_load_4d(stg + t * kStageBytes, &maps.skip, skfull + 8 * t, 0, (c_sp * 2 + static_cast<int>(rank)) * kStripW, c_y, c_n);
+      }
+      __syncwarp();
+      ++c_idx;
+      if (++c_y >= c_y1) {
+        c_item += npairs;
+        c_ok = c_item < p.items;
+        if (c_ok) pair_trunk_decode(p, c_item, c_n, c_sp, c_y, c_y1);
+      }
+    };
+    if (lead_warp) for (int i = 0; i < Cfg::kSkipAhead; ++i) prefetch_skip();
+    for (int item = pair; item < p.items; item += npairs) {
+      int n, sp, y0, y1;
+      pair_trunk_decode(p, item, n, sp, y0, y1);
+      const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      for (int y = y0; y < y1; ++y, ++acc) {
+        const uint32_t stage = acc % AS;
+        const uint32_t os = acc % OS;
+        uint8_t* row = my_row + os * kStageBytes;
+        if (has_skip) {
+          ptx::mbar_wait(skfull + 8 * os, (acc / OS) & 1);
+        } else {
+          if (lead_warp) {
+            if (ptx::elect_one()) ptx::bulk_wait_read<OS - 1>();
+            __syncwarp();
+          }
+          ptx::named_bar_sync(1, kEpiThreads);
+        }
+        ptx::mbar_wait(tfull + 8 * stage, (acc / AS) & 1);
+        ptx::tc_fence_after_sync();
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 64 + half * 32, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + 8 * stage);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cidx = ((half * 4 + q) ^ sw) << 4;
+          uint4 sk = make_uint4(0, 0, 0, 0);
+          if (has_skip) sk = *reinterpret_cast<const uint4*>(row + cidx);
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = q * 8 + e * 2;
+            float s0 = 0.f, s1 = 0.f;
+            if (has_skip) {
+              const uint32_t sw32 = reinterpret_cast<const uint32_t*>(&sk)[e];
+              const __half2 hs = *reinterpret_cast<const __half2*>(&sw32);
+              s0 = __low2float(hs);
+              s1 = __high2float(hs);
+            }
+            const float f0 = epi_apply(__uint_as_float(v[j]), p.epi, p.param, 0.f, s0);
+            const float f1 = epi_apply(__uint_as_float(v[j + 1]), p.epi, p.param, 0.f, s1);
+            const __half2 hv = __floats2half2_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          *reinterpret_cast<uint4*>(row + cidx) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(2, kEpiThreads);
+        if (lead_warp) {
+          if (ptx::elect_one()) {
+            ptx::tma_store_4d(omap, stg + os * kStageBytes, 0, x0, y, n);
+            ptx::bulk_commit();
+            // the tile the next prefetch targets was stored kOutStages - kSkipAhead rows ago: everything older
+            // than the (kOutStages - kSkipAhead) most recent stores must have read its tile
+            if (has_skip) ptx::bulk_wait_read<OS - Cfg::kSkipAhead>();
+          }
+          __syncwarp();
+          prefetch_skip();
+        }
+      }
+    }
+    if (lead_warp) {
+      if (ptx::elect_one()) ptx::bulk_wait<0>();
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 }  // namespace moe

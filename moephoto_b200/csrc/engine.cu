@@ -61,7 +61,9 @@ struct MoeEngine {
   int simt = 0;
   int cur_feat = 64;       // real filter count of the model being run (48 for NetDN) — FLOP accounting only
   bool smem_attr_set = false, head_attr_set = false, pair_attr_set = false;
-  int no_pair = 0;         // 1 = keep the upsample convs on the single-CTA kernel (A/B switch)
+  int no_pair = 0;         // 1 = keep every conv on the single-CTA kernel (A/B switch)
+  int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
+  bool pair_trunk_attr_set = false;
   // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3 r=1, 2 heads, 3 upsample conv3x3
   bool profiling = false;
   struct Span { int cls; cudaEvent_t a, b; double work; };
@@ -142,6 +144,21 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
     return check_launch(e, "conv3x3_simt_kernel");
   }
   const bool pair_path = r == 2 && epi == EPI_BIAS_PRELU && !e->no_pair && e->sm_count >= 4;
+  const bool pair_trunk = r == 1 && epi != EPI_BIAS_PRELU && !e->no_pair && !e->no_pair_trunk && e->sm_count >= 4;
+  if (pair_trunk) {
+    // CTA pairs for the 64 -> 64 convolutions: 256 px x 64 channels per MMA, conv_pair.cuh
+    const int npairs = e->sm_count / 2;
+    const int strips1 = (W + kStripW - 1) / kStripW;
+    p.strips = (strips1 + 1) / 2;                            // strip PAIRS
+    const int64_t base_items = static_cast<int64_t>(N) * p.strips;
+    int nseg = static_cast<int>((4ll * npairs + base_items - 1) / base_items);
+    nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
+    p.seg_rows = (H + nseg - 1) / nseg;
+    p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+    const int64_t items = base_items * p.nseg;
+    if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
+    p.items = static_cast<int>(items);
+  }
   if (pair_path) {
     // CTA pairs (cta_group::2): 256 px x 128 channels per MMA, conv_pair.cuh
     const int npairs = (e->sm_count / 2) & ~1;              // even, so a pair keeps its chunk group (weights stay resident)
@@ -159,7 +176,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   const int ncg = r * r;                                    // one 64-channel chunk per CTA
   const int G = std::max(ncg, e->sm_count / ncg * ncg);    // CTAs; multiple of ncg so a CTA keeps its chunk
   int grid = 0;
-  if (!pair_path) {
+  if (!pair_path && !pair_trunk) {
     p.strips = (W + kStripW - 1) / kStripW;
     const int64_t base_items = static_cast<int64_t>(N) * p.strips * ncg;
     int nseg = static_cast<int>((4ll * G + base_items - 1) / base_items);
@@ -194,6 +211,15 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
                 static_cast<cuuint64_t>(r) * Wo * 128, Ho * Wo * 128, kStripW);
   }
   if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d H=%d W=%d r=%d", (int)cr, N, H, W, r);
+  if (pair_trunk) {
+    if (!e->pair_trunk_attr_set) {
+      MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairTrunkCfg::kSmemBytes));
+      e->pair_trunk_attr_set = true;
+    }
+    const int npairs = static_cast<int>(std::min<int64_t>(e->sm_count / 2, p.items));
+    conv3x3_pair_trunk_kernel<<<2 * npairs, kConvThreads, PairTrunkCfg::kSmemBytes, st>>>(maps, p);
+    return check_launch(e, "conv3x3_pair_trunk_kernel");
+  }
   if (pair_path) {
     if (!e->pair_attr_set) {
       MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
@@ -391,6 +417,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   if (!e) return fail(MOE_ERR_INVALID, "engine is null");
   e->simt = simt & 1;
   e->no_pair = (simt >> 1) & 1;
+  e->no_pair_trunk = (simt >> 2) & 1;
   return MOE_OK;
 }
 
@@ -517,7 +544,8 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     e->cur_feat = m->feat;
     {
     Timed timed(e, st, 0, static_cast<double>(N) * H * W * (2 + 128));     // bytes: read 1 fp16, write 64 fp16
-    conv_first_kernel<<<grid_for(static_cast<int64_t>(N) * H * ((W + 3) / 4) * 8, 256, e->sm_count), 256, 0, st>>>(fp);
+    if (H > 65535 || N > 65535) return fail(MOE_ERR_INVALID, "tile too tall for the conv_input grid");
+    conv_first_kernel<<<dim3((((W + 3) / 4) * 8 + 255) / 256, H, N), 256, 0, st>>>(fp);
     }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 

@@ -37,15 +37,15 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p)
   __shared__ float ws[9 * 64];
   for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) ws[i] = p.w[i];
   __syncthreads();
-  const int gw = (p.W + 3) >> 2;                                   // 4-pixel groups per row
-  const int64_t total = static_cast<int64_t>(p.N) * p.H * gw * 8;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx & 7);
-    const int64_t grp = idx >> 3;
-    const int x = static_cast<int>(grp % gw) * 4;
-    const int y = static_cast<int>((grp / gw) % p.H);
-    const int n = static_cast<int>(grp / (static_cast<int64_t>(gw) * p.H));
+  // grid: x = 4-pixel groups of a row (8 threads each), y = row, z = plane — no integer divisions per thread
+  const int gw = (p.W + 3) >> 2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= gw * 8) return;
+  {
+    const int g = t & 7;
+    const int x = (t >> 3) * 4;
+    const int y = blockIdx.y;
+    const int n = blockIdx.z;
     float win[3][6];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {

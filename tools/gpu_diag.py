@@ -118,10 +118,10 @@ def golden_suite(eng):
 def timing(eng):
   sys.path.insert(0, os.path.join(ROOT, 'tests'))
   import helpers as Hh
-  for key, scale, shape, no_pair in (('a2', 2, (3, 1080, 1920), False), ('a4', 4, (3, 2160, 3840), True), ('a4', 4, (3, 2160, 3840), False)):
+  for key, scale, shape, no_pt in (('a2', 2, (3, 1080, 1920), False), ('a4', 4, (3, 2160, 3840), True), ('a4', 4, (3, 2160, 3840), False)):
     try:
-      eng.set_conv_path(simt=False, no_pair=no_pair)
-      say('[time] upsample convs on CTA pairs: %s' % (not no_pair))
+      eng.set_conv_path(simt=False, no_pair=False, no_pair_trunk=no_pt)
+      say('[time] trunk convs on CTA pairs: %s (upsample convs always)' % (not no_pt))
       sd = Hh.load_weights(key)
       opt = runSR.getOpt({'model': 'a', 'scale': scale}, weights=sd)
       x = torch.rand(shape, device='cuda').half()
