@@ -94,7 +94,8 @@ int moe_engine_profile(MoeEngine* e, int enable);
 int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t launches[4]);
 /* bit 0: 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (debug cross-check);
  * bit 1: 1 = keep every convolution on the single-CTA kernel instead of CTA pairs (A/B switch);
- * bit 2: 1 = only the 64->64 trunk convolutions stay on the single-CTA kernel */
+ * bit 2: 1 = only the 64->64 trunk convolutions stay on the single-CTA kernel;
+ * bit 3: 1 = do not fuse the last upsample convolution with the heads' dot products */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
 
 /* ---- model -------------------------------------------------------------------------------- */

@@ -1,0 +1,344 @@
+// Last upsample convolution of a branch FUSED with the dot-product half of the Conv3x3(64,1) head
+// (models.py:29-33 + :130/:151).  conv3x3_pair_kernel writes PReLU(PixelShuffle(conv+b)) to HBM as 64 fp16
+// channels per output pixel (128 B) only for head_tc_kernel to read it back and reduce it to nine numbers.
+// Here the reduction happens while the pixel is still in shared memory:
+//   * the epilogue writes its fp16 tile to the swizzled staging tile exactly as before — which is exactly the
+//     layout of a K-major UMMA A operand — and, instead of a TMA store, a SECOND tcgen05.mma stream
+//     (M = 256 over the pair, N = 16 = 9 taps padded, K = 64) multiplies it with the head filter:
+//     P_t(Y,X) = <w_head[t], act(Y,X,:)>, fp32 in TMEM;
+//   * four reader warps move P (9 floats per pixel) to a planar fp32 buffer: 36 B per pixel instead of 128 B,
+//     and the 2 x 12.8 GB intermediate tensors of an a4 tile are never written or read;
+//   * head_stencil_kernel (kernels_simt.cuh) then sums the 3x3 stencil of P_u + P_r, rounds, blends, stores.
+// Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader) / weight handshake (peer), 2..9 epilogue,
+// 10 head-MMA issuer (leader), 11..14 P readers.  TMEM: 3 accumulator stages x 128 columns + 2 P stages x 32.
+#pragma once
+#include "conv_pair.cuh"
+#include "kernels_simt.cuh"
+
+namespace moe {
+
+struct PairHeadParams {
+  ConvParams c;            // the convolution (r = 2, EPI_BIAS_PRELU); c.out is unused
+  const uint8_t* head_img; // [16 rows][128 B] swizzled fp16: rows 0..8 = the 9 taps of THIS branch's head filter
+  float* pbuf;             // [N][9][2H][2W] fp32
+};
+
+constexpr int kPairHeadThreads = 15 * 32;
+
+struct PairHeadCfg {
+  static constexpr int kSlots = 6;
+  static constexpr int kAccStages = 3;
+  static constexpr int kPStages = 2;
+  static constexpr uint32_t kPCol0 = kAccStages * 128;     // 384
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kChunkImgBytes + 2 * kStageBytes + 1024 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairHeadThreads, 1)
+conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadParams hp)
+{
+  using Cfg = PairHeadCfg;
+  constexpr int S = Cfg::kSlots, AS = Cfg::kAccStages, PS = Cfg::kPStages;
+  const ConvParams& p = hp.c;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t ring = base;
+  const uint32_t wsm = ring + S * kSlotBytes;
+  const uint32_t stg = wsm + kChunkImgBytes;                       // two staging tiles = the two chunks of a row
+  const uint32_t hsm = stg + 2 * kStageBytes;                       // this CTA's 8 rows of the head filter (1 KB)
+  const uint32_t bars = hsm + 1024;
+  const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
+  const uint32_t staged = tempty + 8 * AS, pfull = staged + 8 * PS, pempty = pfull + 8 * PS;
+  const uint32_t wbar = pempty + 8 * PS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
+  const uint32_t bias_sm = bars + 512;                              // 128 floats, 16-byte aligned
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
+  uint8_t* stg_ptr = smem + (stg - base);
+  float* bias_ptr = reinterpret_cast<float*>(smem + (bias_sm - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader_cta = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int g_fixed = pair & 1;                   // npairs is even (host): a pair keeps its chunk group
+  const int my_chunk = g_fixed * 2 + static_cast<int>(rank);
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
+    for (int i = 0; i < AS; ++i) { ptx::mbar_init(tfull + 8 * i, 1); ptx::mbar_init(tempty + 8 * i, 2 * kEpiWarps); }
+    for (int i = 0; i < PS; ++i) { ptx::mbar_init(staged + 8 * i, 2); ptx::mbar_init(pfull + 8 * i, 1); ptx::mbar_init(pempty + 8 * i, 2 * 4); }
+    ptx::mbar_init(wbar, 1);
+    ptx::mbar_init(wpeer, 1);
+    ptx::mbar_init(dbar, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&maps.in);
+  }
+  for (int i = tid; i < 128; i += kPairHeadThreads) bias_ptr[i] = p.bias[g_fixed * 128 + i];
+  if (warp == 1) ptx::tmem_alloc_pair(tslot, Cfg::kTmemCols);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tslot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(wbar, kChunkImgBytes + 1024);
+      const uint8_t* src = p.w_img + static_cast<size_t>(my_chunk) * kChunkImgBytes;
+      for (int tap = 0; tap < 9; ++tap) ptx::bulk_load_1d(wsm + tap * 8192, src + tap * 8192, 8192, wbar);
+      ptx::bulk_load_1d(hsm, hp.head_img + rank * 1024, 1024, wbar);       // taps 8*rank .. 8*rank+7
+    }
+    __syncwarp();
+    uint32_t ld = 0;
+    for (int item = pair; item < p.items; item += npairs) {
+      int g, n, sp, y0, y1;
+      pair_decode_item(p, item, g, n, sp, y0, y1);
+      const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
+        const uint32_t slot = ld % S;
+        ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
+        if (ptx::elect_one()) {
+          if (leader_cta) ptx::mbar_expect_tx(full + 8 * slot, 2 * kRowBytes);
+          ptx::tma_load_4d_pair(ring + slot * kSlotBytes, &maps.in, ptx::mapa(full + 8 * slot, 0), 0, x0 - 1, yy, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (!leader_cta) {
+      ptx::mbar_wait(wbar, 0);
+      if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(wpeer, 0));
+      __syncwarp();
+    } else {
+      // ---------------------------------------------------------- leader: main MMA stream (as conv3x3_pair_kernel, 3 stages)
+      constexpr uint32_t idesc = ptx::idesc_f16_f32(256, 128);
+      const uint64_t bdesc0 = ptx::smem_desc_sw128(wsm, 1024, 0);
+      const uint64_t adesc0 = ptx::smem_desc_sw128(ring, 1024, 0);
+      ptx::mbar_wait(wbar, 0);
+      ptx::mbar_wait(wpeer, 0);
+      ptx::tc_fence_after_sync();
+      uint32_t cons = 0, acc = 0;
+      for (int item = pair; item < p.items; item += npairs) {
+        int g, n, sp, y0, y1;
+        pair_decode_item(p, item, g, n, sp, y0, y1);
+        const int nrows = y1 - y0;
+        ptx::mbar_wait(full + 8 * (cons % S), (cons / S) & 1);
+        ptx::mbar_wait(full + 8 * ((cons + 1) % S), ((cons + 1) / S) & 1);
+        for (int j = 0; j < nrows; ++j) {
+          const uint32_t l2 = cons + j + 2;
+          ptx::mbar_wait(full + 8 * (l2 % S), (l2 / S) & 1);
+          const uint32_t stage = acc % AS;
+          ptx::mbar_wait(tempty + 8 * stage, ((acc / AS) & 1) ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + stage * 128;
+          const uint64_t arow0 = adesc0 + static_cast<uint64_t>(((cons + j) % S) * (kSlotBytes >> 4));
+          const uint64_t arow1 = adesc0 + static_cast<uint64_t>(((cons + j + 1) % S) * (kSlotBytes >> 4));
+          const uint64_t arow2 = adesc0 + static_cast<uint64_t>(((cons + j + 2) % S) * (kSlotBytes >> 4));
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint64_t arow = dy == 0 ? arow0 : (dy == 1 ? arow1 : arow2);
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, (dy | dx | k) != 0);
+                }
+              }
+            }
+            ptx::mma_commit_pair_mc(tfull + 8 * stage, 3);
+            ptx::mma_commit_pair_mc(empty + 8 * ((cons + j) % S), 3);
+          }
+          __syncwarp();
+          ++acc;
+        }
+        if (ptx::elect_one()) {
+          ptx::mma_commit_pair_mc(empty + 8 * ((cons + nrows) % S), 3);
+          ptx::mma_commit_pair_mc(empty + 8 * ((cons + nrows + 1) % S), 3);
+        }
+        __syncwarp();
+        cons += nrows + 2;
+      }
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ epilogue: accumulator -> fp16 staging tile (= head A operand)
+    const int lgrp = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    const int L = lgrp * 32 + lane;
+    const bool lead_warp = (warp == 2);
+    uint8_t* my_row = stg_ptr + ch * kStageBytes + L * 128;
+    const int sw = L & 7;
+    const uint32_t tempty_leader = ptx::mapa(tempty, 0);
+    const uint32_t staged_leader = ptx::mapa(staged, 0);
+    const float* my_bias = bias_ptr + ch * 64;
+    uint32_t acc = 0;
+    for (int item = pair; item < p.items; item += npairs) {
+      int g, n, sp, y0, y1;
+      pair_decode_item(p, item, g, n, sp, y0, y1);
+      for (int y = y0; y < y1; ++y, ++acc) {
+        const uint32_t stage = acc % AS;
+        ptx::mbar_wait(tfull + 8 * stage, (acc / AS) & 1);
+        ptx::tc_fence_after_sync();
+        uint4 pk[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 128 + ch * 64 + h * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = q * 8 + e * 2;
+              const float f0 = epi_apply(__uint_as_float(v[j]), EPI_BIAS_PRELU, p.param, bb[e * 2], 0.f);
+              const float f1 = epi_apply(__uint_as_float(v[j + 1]), EPI_BIAS_PRELU, p.param, bb[e * 2 + 1], 0.f);
+              const __half2 hv = __floats2half2_rn(f0, f1);
+              w[e] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            pk[h * 4 + q] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + 8 * stage);
+        // the staging tiles are the A operand of the previous row's head MMAs: wait until those completed
+        if (acc > 0) ptx::mbar_wait(pfull + 8 * ((acc - 1) % PS), ((acc - 1) / PS) & 1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = pk[c];
+        ptx::fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core's async proxy
+        ptx::named_bar_sync(2, kEpiThreads);
+        if (lead_warp) {
+          if (ptx::elect_one()) ptx::mbar_arrive_cluster_release(staged_leader + 8 * (acc % PS));
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 10) {
+    if (leader_cta) {
+      // ---------------------------------------------------------- leader: head MMA stream, P = staging tile x head filter
+      constexpr uint32_t idesc = ptx::idesc_f16_f32(256, 16);
+      const uint64_t a0 = ptx::smem_desc_sw128(stg, 1024, 0);
+      const uint64_t b0 = ptx::smem_desc_sw128(hsm, 1024, 0);
+      ptx::mbar_wait(wbar, 0);
+      ptx::mbar_wait(wpeer, 0);
+      uint32_t acc = 0;
+      for (int item = pair; item < p.items; item += npairs) {
+        int g, n, sp, y0, y1;
+        pair_decode_item(p, item, g, n, sp, y0, y1);
+        for (int y = y0; y < y1; ++y, ++acc) {
+          const uint32_t ps = acc % PS;
+          ptx::mbar_wait_cluster(staged + 8 * ps, (acc / PS) & 1);      // both CTAs' staging tiles are written
+          ptx::mbar_wait(pempty + 8 * ps, ((acc / PS) & 1) ^ 1);        // both CTAs' readers drained this P stage
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::mma_f16_ss_pair(tmem_base + Cfg::kPCol0 + ps * 32 + c * 16, a0 + (c * (kStageBytes >> 4) + k * 2), b0 + k * 2, idesc, k != 0);
+            ptx::mma_commit_pair_mc(pfull + 8 * ps, 3);
+          }
+          __syncwarp();
+        }
+      }
+      if (ptx::elect_one()) ptx::mma_commit_pair(dbar);     // drain (both MMA streams complete in issue order per thread; see below)
+      __syncwarp();
+      ptx::mbar_wait(dbar, 0);
+    }
+  } else {
+    // ------------------------------------------------------------ P readers (warps 11..14): TMEM -> planar fp32 in HBM
+    const int lgrp = warp & 3;
+    const int L = lgrp * 32 + lane;
+    const uint32_t pempty_leader = ptx::mapa(pempty, 0);
+    const int Ho = p.H * 2, Wo = p.W * 2;
+    const size_t plane = static_cast<size_t>(Ho) * Wo;
+    uint32_t acc = 0;
+    for (int item = pair; item < p.items; item += npairs) {
+      int g, n, sp, y0, y1;
+      pair_decode_item(p, item, g, n, sp, y0, y1);
+      const int x = (sp * 2 + static_cast<int>(rank)) * kStripW + L;
+      for (int y = y0; y < y1; ++y, ++acc) {
+        const uint32_t ps = acc % PS;
+        ptx::mbar_wait(pfull + 8 * ps, (acc / PS) & 1);
+        ptx::tc_fence_after_sync();
+        uint32_t v0[16], v1[16];
+        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + Cfg::kPCol0 + ps * 32, v0);
+        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + Cfg::kPCol0 + ps * 32 + 16, v1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(pempty_leader + 8 * ps);
+        if (x < p.W) {
+          // chunk c of this pair's group g is sub-pixel (i, j) = (g, c): output pixel (2y + g, 2x + c)
+          float* dst = hp.pbuf + static_cast<size_t>(n) * 9 * plane + static_cast<size_t>(2 * y + g_fixed) * Wo + 2 * x;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            *reinterpret_cast<float2*>(dst + t * plane) = make_float2(__uint_as_float(v0[t]), __uint_as_float(v1[t]));
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// out(Y,X) = round16( sum_{dy,dx} (P_u + P_r)[dy*3+dx](Y+dy-1, X+dx-1) ), zero outside the computed rectangle,
+// then the seam blend and the canvas store of head_blend_kernel / head_tc_kernel.  One thread per output pixel.
+struct HeadStencilParams {
+  HeadParams g;            // geometry, seam and canvas (u/r/wu/wr unused)
+  const float* pu;         // [N][9][H][W]
+  const float* pr;
+};
+
+__global__ void __launch_bounds__(256) head_stencil_kernel(const HeadStencilParams p)
+{
+  const HeadParams& g = p.g;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, n = blockIdx.z;
+  if (x >= g.W) return;
+  const int cy = g.oy + y, cx = g.ox + x;
+  if (cy < g.keep_y0 || cy >= g.keep_y1 || cx < g.keep_x0 || cx >= g.keep_x1) return;
+  const size_t plane = static_cast<size_t>(g.H) * g.W;
+  const float* bu = p.pu + static_cast<size_t>(n) * 9 * plane;
+  const float* br = p.pr + static_cast<size_t>(n) * 9 * plane;
+  float hsum[3];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    float t3[3] = {0.f, 0.f, 0.f};
+    if (yy >= 0 && yy < g.H) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x + dx - 1;
+        if (xx >= 0 && xx < g.W) {
+          const size_t o = static_cast<size_t>(dy * 3 + dx) * plane + static_cast<size_t>(yy) * g.W + xx;
+          t3[dx] = __ldg(bu + o) + __ldg(br + o);
+        }
+      }
+    }
+    hsum[dy] = (t3[0] + t3[1]) + t3[2];
+  }
+  float v = h_round((hsum[0] + hsum[1]) + hsum[2]);
+  __half* dst = g.canvas + n * g.plane_stride + static_cast<int64_t>(cy) * g.row_stride + cx;
+  if (cy < g.blend_y1 || cx < g.blend_x1) {
+    const float old = __half2float(*dst);
+    if (cy < g.blend_y1) v = h_round(old + h_round(g.ramp[cy - g.ramp_y0] * h_round(v - old)));
+    if (cx < g.blend_x1) v = h_round(old + h_round(g.ramp[cx - g.ramp_x0] * h_round(v - old)));
+  }
+  *dst = __float2half_rn(v);
+}
+
+}  // namespace moe

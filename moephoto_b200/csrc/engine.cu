@@ -17,6 +17,7 @@
 #include "blob.h"
 #include "conv_tc.cuh"
 #include "conv_pair.cuh"
+#include "conv_pair_head.cuh"
 #include "kernels_simt.cuh"
 #include "head_tc.cuh"
 
@@ -63,6 +64,8 @@ struct MoeEngine {
   bool smem_attr_set = false, head_attr_set = false, pair_attr_set = false;
   int no_pair = 0;         // 1 = keep every conv on the single-CTA kernel (A/B switch)
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
+  int no_fuse = 0;         // 1 = last upsample conv and heads stay separate kernels (conv3x3_pair_kernel + head_tc_kernel)
+  bool pair_head_attr_set = false;
   bool pair_trunk_attr_set = false;
   // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3 r=1, 2 heads, 3 upsample conv3x3
   bool profiling = false;
@@ -235,6 +238,46 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   }
   conv3x3_tc_kernel<<<grid, kConvThreads, ConvCfg::kSmemBytes, st>>>(maps, p);
   return check_launch(e, "conv3x3_tc_kernel");
+}
+
+// ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
+int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, int N, int H, int W,
+                     float slope, const uint8_t* head_img, float* pbuf)
+{
+  PairHeadParams hp{};
+  ConvParams& p = hp.c;
+  p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
+  p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope;
+  hp.head_img = head_img; hp.pbuf = pbuf;
+  Timed timed(e, st, 3, 2.0 * 9 * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
+  const int npairs_max = (e->sm_count / 2) & ~1;
+  const int strips1 = (W + kStripW - 1) / kStripW;
+  p.strips = (strips1 + 1) / 2;
+  const int64_t base_items = 2ll * N * p.strips;
+  int nseg = static_cast<int>((4ll * npairs_max + base_items - 1) / base_items);
+  nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
+  p.seg_rows = (H + nseg - 1) / nseg;
+  p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+  const int64_t items = base_items * p.nseg;
+  if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
+  p.items = static_cast<int>(items);
+  ConvMaps maps;
+  memset(&maps, 0, sizeof maps);
+  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  const cuuint64_t strides[3] = {128, dims[1] * 128, dims[1] * dims[2] * 128};
+  const cuuint32_t box[4] = {64, kRowPx, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = e->encode(&maps.in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  if (!e->pair_head_attr_set) {
+    MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairHeadCfg::kSmemBytes));
+    e->pair_head_attr_set = true;
+  }
+  const int npairs = static_cast<int>(std::min<int64_t>(npairs_max, p.items));
+  conv3x3_pair_head_kernel<<<2 * npairs, kPairHeadThreads, PairHeadCfg::kSmemBytes, st>>>(maps, hp);
+  return check_launch(e, "conv3x3_pair_head_kernel");
 }
 
 // ---- the two heads + blend + store on the tensor cores (head_tc.cuh) ---------------------------
@@ -418,6 +461,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   e->simt = simt & 1;
   e->no_pair = (simt >> 1) & 1;
   e->no_pair_trunk = (simt >> 2) & 1;
+  e->no_fuse = (simt >> 3) & 1;
   return MOE_OK;
 }
 
@@ -559,7 +603,25 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
 
     // the two upsample stacks u(out) and convt_R1(t)                          models.py:29-33,125-154
     const __half* head_in[2] = {bufA, bufT};
-    if (m->n_up == 1) {
+    const bool fuse = !e->simt && !e->no_pair && !e->no_fuse && m->n_up >= 1 && m->r == 2 && e->sm_count >= 4;
+    const size_t pbytes = align_up(static_cast<size_t>(N) * 9 * (H * sc) * (W * sc) * sizeof(float), 1024);
+    float* pbuf[2] = {nullptr, nullptr};
+    if (fuse && m->n_up == 1) {
+      for (int b = 0; b < 2; ++b) {
+        pbuf[b] = reinterpret_cast<float*>(up0 + b * pbytes);
+        if ((rc = launch_conv_head(e, st, b ? bufT : bufA, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, m->scalars[14 + 2 * b],
+                                   m->d_head_img + b * 2048, pbuf[b])) != MOE_OK) return rc;
+      }
+    } else if (fuse && m->n_up == 2) {
+      __half* s1 = reinterpret_cast<__half*>(up0);                 // 4 units, shared by both branches
+      for (int b = 0; b < 2; ++b) {
+        pbuf[b] = reinterpret_cast<float*>(up0 + 4 * unit + b * pbytes);
+        if ((rc = launch_conv(e, st, b ? bufT : bufA, s1, nullptr, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, 2,
+                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b])) != MOE_OK) return rc;
+        if ((rc = launch_conv_head(e, st, s1, m->up_img[2 * b + 1], m->up_bias[2 * b + 1], N, 2 * H, 2 * W, m->scalars[14 + 2 * b + 1],
+                                   m->d_head_img + b * 2048, pbuf[b])) != MOE_OK) return rc;
+      }
+    } else if (m->n_up == 1) {
       const size_t usz = unit * m->r * m->r;
       for (int b = 0; b < 2; ++b) {
         __half* dst = reinterpret_cast<__half*>(up0 + b * usz);
@@ -589,7 +651,14 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     for (int i = 0; i < plan->pad_sc; ++i) hp.ramp[i] = plan->ramp[i];
     hp.canvas = static_cast<__half*>(canvas);
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
-    if (e->simt) {
+    if (fuse) {
+      HeadStencilParams sp{};
+      sp.g = hp; sp.pu = pbuf[0]; sp.pr = pbuf[1];
+      dim3 sgrid((hp.W + 255) / 256, hp.H, N);
+      if (sgrid.y > 65535u || sgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the stencil kernel grid");
+      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (2 * 36 + 2));   // bytes: two 9-float reads, one fp16 write
+      head_stencil_kernel<<<sgrid, 256, 0, st>>>(sp);
+    } else if (e->simt) {
       dim3 hgrid((hp.W + 127) / 128, hp.H, N);
       if (hgrid.y > 65535u || hgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the head kernel grid");
       Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (2 * 128 + 2));   // bytes: two 64-ch fp16 reads, one fp16 write

@@ -34,9 +34,6 @@ struct FirstParams {
 // a warp writes four full 128-byte pixels); bandwidth-bound: 2 B read, 128 B written per pixel.
 __global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p)
 {
-  __shared__ float ws[9 * 64];
-  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) ws[i] = p.w[i];
-  __syncthreads();
   // grid: x = 4-pixel groups of a row (8 threads each), y = row, z = plane — no integer divisions per thread
   const int gw = (p.W + 3) >> 2;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,11 +55,14 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p)
         win[dy][dx] = (sy >= 0 && sx >= 0) ? __half2float(p.img[n * p.plane_stride + sy * p.row_stride + sx]) : 0.f;
       }
     }
-    float wreg[9][8];
+    float wreg[9][8];                      // this thread's 8 output channels of every tap (L1-resident, 2.3 KB in all)
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) wreg[t][c] = ws[t * 64 + g * 8 + c];
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * 64 + g * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + t * 64 + g * 8 + 4));
+      wreg[t][0] = w0.x; wreg[t][1] = w0.y; wreg[t][2] = w0.z; wreg[t][3] = w0.w;
+      wreg[t][4] = w1.x; wreg[t][5] = w1.y; wreg[t][6] = w1.z; wreg[t][7] = w1.w;
+    }
     const size_t pix0 = (static_cast<size_t>(n) * p.H + y) * p.W + x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

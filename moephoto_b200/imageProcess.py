@@ -62,8 +62,9 @@ class Engine:
     d['conv3x3'] = tuple(a + b for a, b in zip(d['conv_trunk'], d['conv_up']))      # every 3x3 tensor-core convolution
     return d
 
-  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False):
-    _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(no_pair)) << 1) | (int(bool(no_pair_trunk)) << 2)))
+  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False):
+    _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(no_pair)) << 1) | (int(bool(no_pair_trunk)) << 2) |
+                                                 (int(bool(no_fuse)) << 3)))
 
   def get_workspace(self, nbytes):
     if self.workspace is None or self.workspace.numel() < nbytes:

@@ -120,8 +120,8 @@ def timing(eng):
   import helpers as Hh
   for key, scale, shape, no_pt in (('a2', 2, (3, 1080, 1920), False), ('a4', 4, (3, 2160, 3840), True), ('a4', 4, (3, 2160, 3840), False)):
     try:
-      eng.set_conv_path(simt=False, no_pair=False, no_pair_trunk=no_pt)
-      say('[time] trunk convs on CTA pairs: %s (upsample convs always)' % (not no_pt))
+      eng.set_conv_path(simt=False, no_fuse=no_pt)
+      say('[time] last upsample conv fused with the head dot products: %s' % (not no_pt))
       sd = Hh.load_weights(key)
       opt = runSR.getOpt({'model': 'a', 'scale': scale}, weights=sd)
       x = torch.rand(shape, device='cuda').half()
