@@ -308,3 +308,42 @@ def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
       assert np.abs(out[i].astype(np.int64) - (want.astype(np.int64) & 0xFFFF)).max() <= 140        # 2e-3 * 65536
   finally:
     config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
+
+
+@pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True)])
+@pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled'])
+def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags):
+    """the A/B switches keep the single-CTA conv kernel, the unfused CTA-pair kernel and head_tc_kernel alive;
+    each variant is held to the same tolerance as the default path (CTA pairs + fused head)"""
+    c = H.load_case(name)
+    y_default = H.run_case_engine(c)
+    engine.set_conv_path(**flags)
+    try:
+        y = H.run_case_engine(c)
+    finally:
+        engine.set_conv_path()
+    orc = H.run_case_oracle(c, mode='f16io')
+    assert np.abs(y - orc).max() <= 1e-3
+    assert H.psnr(y, c['ref']) >= 60.0
+    assert np.abs(y - y_default).max() <= 1e-3
+
+
+def test_fused_path_at_4k_tile_width(engine):
+    """one reference tile of the bench workload shape in miniature height (3 x 64 x 968, a4): the CTA-pair kernels with
+    an odd number of 128-px strips (968 = 7.56 strips -> 4 pairs, the last CTA half empty), checked against the SIMT path"""
+    from moephoto_b200 import imageProcess as IP
+    from moephoto_b200.config import config
+    opt = _sr_opt('a4', 4)
+    try:
+        g = torch.Generator().manual_seed(17)
+        x = torch.nn.functional.interpolate(torch.rand(1, 3, 8, 121, generator=g), size=(64, 968), mode='bicubic')[0].clamp(0, 1).half().cuda()
+        y = IP.doCrop(opt, x)
+        engine.set_conv_path(simt=True)
+        try:
+            y_simt = IP.doCrop(opt, x)
+        finally:
+            engine.set_conv_path()
+        assert tuple(y.shape) == (3, 256, 3872)
+        assert (y.float() - y_simt.float()).abs().max().item() <= 1e-3
+    finally:
+        config.freeMemOverride = None
