@@ -320,7 +320,7 @@ def main():
             'd2h_bytes_per_step': H_IN * SCALE * W_IN * SCALE * 3, 'path': 'moe_enhance_host (C ABI, pinned host uint8 in/out)' if world == 1 else
             'toTorch -> sharded doCrop (NCCL) -> moe_to_output -> pinned host'},
     'gpu_launches': launches,
-    'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel + conv3x3_pair_kernel (all %d 3x3-convolution launches of rank 0 in the timed region)' % conv_n,
+    'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_pair_trunk_kernel + conv3x3_pair_kernel + conv3x3_pair_head_kernel (all %d 3x3-convolution launches of rank 0 in the timed region)' % conv_n,
                  'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'peak_source': pk['src'],
                  'traffic': traffic, 'avg_launch_ms': conv_ms / max(1, conv_n),
                  'algorithmic_flops_per_launch': conv_flops / max(1, conv_n),
