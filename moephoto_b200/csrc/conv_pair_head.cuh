@@ -7,7 +7,8 @@
 //     (M = 256 over the pair, N = 16 = 9 taps padded, K = 64) multiplies it with the head filter:
 //     P_t(Y,X) = <w_head[t], act(Y,X,:)>, fp32 in TMEM;
 //   * four reader warps move P (9 floats per pixel) to a planar fp32 buffer: 36 B per pixel instead of 128 B,
-//     and the 2 x 12.8 GB intermediate tensors of an a4 tile are never written or read;
+//     and the 2 x 12.8 GB intermediate tensors of an a4 tile are never written or read; the second branch's
+//     launch adds its P onto the first's, so one array leaves the pair of launches;
 //   * head_stencil_kernel (kernels_simt.cuh) then sums the 3x3 stencil of P_u + P_r, rounds, blends, stores.
 // Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader) / weight handshake (peer), 2..9 epilogue,
 // 10 head-MMA issuer (leader), 11..14 P readers.  TMEM: 3 accumulator stages x 128 columns + 2 P stages x 32.
@@ -21,6 +22,7 @@ struct PairHeadParams {
   ConvParams c;            // the convolution (r = 2, EPI_BIAS_PRELU); c.out is unused
   const uint8_t* head_img; // [16 rows][128 B] swizzled fp16: rows 0..8 = the 9 taps of THIS branch's head filter
   float* pbuf;             // [N][9][2H][2W] fp32
+  int accumulate;          // 1: pbuf += P (second branch adds onto the first: the stencil then reads ONE array)
 };
 
 constexpr int kPairHeadThreads = 15 * 32;
@@ -277,9 +279,17 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
         if (x < p.W) {
           // chunk c of this pair's group g is sub-pixel (i, j) = (g, c): output pixel (2y + g, 2x + c)
           float* dst = hp.pbuf + static_cast<size_t>(n) * 9 * plane + static_cast<size_t>(2 * y + g_fixed) * Wo + 2 * x;
+          if (hp.accumulate) {
+            float2 old[9];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            *reinterpret_cast<float2*>(dst + t * plane) = make_float2(__uint_as_float(v0[t]), __uint_as_float(v1[t]));
+            for (int t = 0; t < 9; ++t) old[t] = *reinterpret_cast<const float2*>(dst + t * plane);
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+              *reinterpret_cast<float2*>(dst + t * plane) = make_float2(old[t].x + __uint_as_float(v0[t]), old[t].y + __uint_as_float(v1[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+              *reinterpret_cast<float2*>(dst + t * plane) = make_float2(__uint_as_float(v0[t]), __uint_as_float(v1[t]));
           }
         }
       }
@@ -295,12 +305,11 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   }
 }
 
-// out(Y,X) = round16( sum_{dy,dx} (P_u + P_r)[dy*3+dx](Y+dy-1, X+dx-1) ), zero outside the computed rectangle,
+// out(Y,X) = round16( sum_{dy,dx} P[dy*3+dx](Y+dy-1, X+dx-1) ), P = P_u + P_r,, zero outside the computed rectangle,
 // then the seam blend and the canvas store of head_blend_kernel / head_tc_kernel.  One thread per output pixel.
 struct HeadStencilParams {
   HeadParams g;            // geometry, seam and canvas (u/r/wu/wr unused)
-  const float* pu;         // [N][9][H][W]
-  const float* pr;
+  const float* pu;         // [N][9][H][W]: P_u + P_r (the second branch's kernel accumulated onto the first's)
 };
 
 __global__ void __launch_bounds__(256) head_stencil_kernel(const HeadStencilParams p)
@@ -313,7 +322,6 @@ __global__ void __launch_bounds__(256) head_stencil_kernel(const HeadStencilPara
   if (cy < g.keep_y0 || cy >= g.keep_y1 || cx < g.keep_x0 || cx >= g.keep_x1) return;
   const size_t plane = static_cast<size_t>(g.H) * g.W;
   const float* bu = p.pu + static_cast<size_t>(n) * 9 * plane;
-  const float* br = p.pr + static_cast<size_t>(n) * 9 * plane;
   float hsum[3];
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(256) head_stencil_kernel(const HeadStencilPara
         const int xx = x + dx - 1;
         if (xx >= 0 && xx < g.W) {
           const size_t o = static_cast<size_t>(dy * 3 + dx) * plane + static_cast<size_t>(yy) * g.W + xx;
-          t3[dx] = __ldg(bu + o) + __ldg(br + o);
+          t3[dx] = __ldg(bu + o);
         }
       }
     }

@@ -132,6 +132,29 @@ int grid_for(int64_t threads, int block, int sm_count) {
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(blocks, static_cast<int64_t>(sm_count) * 16)));
 }
 
+// Row segmentation of a persistent kernel: `base_items` strips (x planes x chunk groups) are each cut into nseg
+// row segments and dealt round-robin to `workers` CTAs (or CTA pairs).  The kernel's time is waves x seg_rows
+// (+ ~2 rows of pipeline fill per item), so nseg is chosen to make the item count land just below a multiple of
+// `workers`: e.g. the a4 trunk conv (12 strip pairs, 74 pairs, 2160 rows) ran 4.05 waves of 87 rows = 5 x 87 row times
+// with the old "4 items per worker" rule and runs 6 x 59 with this one.
+void choose_segments(int64_t base_items, int workers, int H, int min_rows, int* seg_rows_out, int* nseg_out)
+{
+  int64_t best_cost = -1;
+  int best_rows = H, best_n = 1;
+  const int max_nseg = std::max(1, H / std::max(1, min_rows));
+  for (int nseg = 1; nseg <= max_nseg; ++nseg) {
+    const int rows = (H + nseg - 1) / nseg;
+    const int n = (H + rows - 1) / rows;
+    const int64_t items = base_items * n;
+    const int64_t waves = (items + workers - 1) / workers;
+    const int64_t cost = waves * (rows + 3);             // +3: two halo rows of pipeline fill and scheduling slack per item
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_rows = rows; best_n = n; }
+    if (items > 64ll * workers) break;
+  }
+  *seg_rows_out = best_rows;
+  *nseg_out = best_n;
+}
+
 // ---- one 3x3 convolution 64 -> 64*r*r ----------------------------------------------------------
 int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, const __half* skip,
                 const uint8_t* w_img, const float* bias, int N, int H, int W, int r, int epi, float param)
@@ -154,10 +177,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
     const int strips1 = (W + kStripW - 1) / kStripW;
     p.strips = (strips1 + 1) / 2;                            // strip PAIRS
     const int64_t base_items = static_cast<int64_t>(N) * p.strips;
-    int nseg = static_cast<int>((4ll * npairs + base_items - 1) / base_items);
-    nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
-    p.seg_rows = (H + nseg - 1) / nseg;
-    p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+    choose_segments(base_items, npairs, H, 8, &p.seg_rows, &p.nseg);
     const int64_t items = base_items * p.nseg;
     if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
     p.items = static_cast<int>(items);
@@ -168,10 +188,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
     const int strips1 = (W + kStripW - 1) / kStripW;
     p.strips = (strips1 + 1) / 2;                            // strip PAIRS
     const int64_t base_items = 2ll * N * p.strips;
-    int nseg = static_cast<int>((4ll * npairs + base_items - 1) / base_items);
-    nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
-    p.seg_rows = (H + nseg - 1) / nseg;
-    p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+    choose_segments(base_items, npairs, H, 8, &p.seg_rows, &p.nseg);
     const int64_t items = base_items * p.nseg;
     if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
     p.items = static_cast<int>(items);
@@ -182,10 +199,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   if (!pair_path && !pair_trunk) {
     p.strips = (W + kStripW - 1) / kStripW;
     const int64_t base_items = static_cast<int64_t>(N) * p.strips * ncg;
-    int nseg = static_cast<int>((4ll * G + base_items - 1) / base_items);
-    nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
-    p.seg_rows = (H + nseg - 1) / nseg;
-    p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+    choose_segments(base_items, G, H, 8, &p.seg_rows, &p.nseg);
     const int64_t items = base_items * p.nseg;
     if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
     p.items = static_cast<int>(items);
@@ -242,22 +256,19 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
 
 // ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
 int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, int N, int H, int W,
-                     float slope, const uint8_t* head_img, float* pbuf)
+                     float slope, const uint8_t* head_img, float* pbuf, int accumulate)
 {
   PairHeadParams hp{};
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
   p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope;
-  hp.head_img = head_img; hp.pbuf = pbuf;
+  hp.head_img = head_img; hp.pbuf = pbuf; hp.accumulate = accumulate;
   Timed timed(e, st, 3, 2.0 * 9 * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
   const int npairs_max = (e->sm_count / 2) & ~1;
   const int strips1 = (W + kStripW - 1) / kStripW;
   p.strips = (strips1 + 1) / 2;
   const int64_t base_items = 2ll * N * p.strips;
-  int nseg = static_cast<int>((4ll * npairs_max + base_items - 1) / base_items);
-  nseg = std::max(1, std::min(nseg, std::max(1, H / 8)));
-  p.seg_rows = (H + nseg - 1) / nseg;
-  p.nseg = (H + p.seg_rows - 1) / p.seg_rows;
+  choose_segments(base_items, npairs_max, H, 8, &p.seg_rows, &p.nseg);
   const int64_t items = base_items * p.nseg;
   if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
   p.items = static_cast<int>(items);
@@ -289,10 +300,7 @@ int launch_head_tc(MoeEngine* e, cudaStream_t st, const MoeModel* m, const HeadP
   p.strips = (hp.W + kHeadStripOut - 1) / kHeadStripOut;
   const int G = e->sm_count;
   const int64_t base_items = static_cast<int64_t>(hp.N) * p.strips;
-  int nseg = static_cast<int>((4ll * G + base_items - 1) / base_items);
-  nseg = std::max(1, std::min(nseg, std::max(1, hp.H / 16)));
-  p.seg_rows = (hp.H + nseg - 1) / nseg;
-  p.nseg = (hp.H + p.seg_rows - 1) / p.seg_rows;
+  choose_segments(base_items, G, hp.H, 16, &p.seg_rows, &p.nseg);
   const int64_t items = base_items * p.nseg;
   if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "head problem too large");
   p.items = static_cast<int>(items);
@@ -589,7 +597,7 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     {
     Timed timed(e, st, 0, static_cast<double>(N) * H * W * (2 + 128));     // bytes: read 1 fp16, write 64 fp16
     if (H > 65535 || N > 65535) return fail(MOE_ERR_INVALID, "tile too tall for the conv_input grid");
-    conv_first_kernel<<<dim3((((W + 3) / 4) * 8 + 255) / 256, H, N), 256, 0, st>>>(fp);
+    conv_first_kernel<<<dim3((W + 127) / 128, H, N), 256, 0, st>>>(fp);
     }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 
@@ -608,18 +616,18 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     float* pbuf[2] = {nullptr, nullptr};
     if (fuse && m->n_up == 1) {
       for (int b = 0; b < 2; ++b) {
-        pbuf[b] = reinterpret_cast<float*>(up0 + b * pbytes);
+        pbuf[b] = reinterpret_cast<float*>(up0);                    // branch R accumulates onto branch u's P
         if ((rc = launch_conv_head(e, st, b ? bufT : bufA, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, m->scalars[14 + 2 * b],
-                                   m->d_head_img + b * 2048, pbuf[b])) != MOE_OK) return rc;
+                                   m->d_head_img + b * 2048, pbuf[b], b)) != MOE_OK) return rc;
       }
     } else if (fuse && m->n_up == 2) {
       __half* s1 = reinterpret_cast<__half*>(up0);                 // 4 units, shared by both branches
       for (int b = 0; b < 2; ++b) {
-        pbuf[b] = reinterpret_cast<float*>(up0 + 4 * unit + b * pbytes);
+        pbuf[b] = reinterpret_cast<float*>(up0 + 4 * unit);          // branch R accumulates onto branch u's P
         if ((rc = launch_conv(e, st, b ? bufT : bufA, s1, nullptr, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, 2,
                               EPI_BIAS_PRELU, m->scalars[14 + 2 * b])) != MOE_OK) return rc;
         if ((rc = launch_conv_head(e, st, s1, m->up_img[2 * b + 1], m->up_bias[2 * b + 1], N, 2 * H, 2 * W, m->scalars[14 + 2 * b + 1],
-                                   m->d_head_img + b * 2048, pbuf[b])) != MOE_OK) return rc;
+                                   m->d_head_img + b * 2048, pbuf[b], b)) != MOE_OK) return rc;
       }
     } else if (m->n_up == 1) {
       const size_t usz = unit * m->r * m->r;
@@ -653,10 +661,10 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
     if (fuse) {
       HeadStencilParams sp{};
-      sp.g = hp; sp.pu = pbuf[0]; sp.pr = pbuf[1];
+      sp.g = hp; sp.pu = pbuf[0];
       dim3 sgrid((hp.W + 255) / 256, hp.H, N);
       if (sgrid.y > 65535u || sgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the stencil kernel grid");
-      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (2 * 36 + 2));   // bytes: two 9-float reads, one fp16 write
+      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (36 + 2));   // bytes: one 9-float read, one fp16 write
       head_stencil_kernel<<<sgrid, 256, 0, st>>>(sp);
     } else if (e->simt) {
       dim3 hgrid((hp.W + 127) / 128, hp.H, N);
