@@ -596,8 +596,10 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     e->cur_feat = m->feat;
     {
     Timed timed(e, st, 0, static_cast<double>(N) * H * W * (2 + 128));     // bytes: read 1 fp16, write 64 fp16
-    if (H > 65535 || N > 65535) return fail(MOE_ERR_INVALID, "tile too tall for the conv_input grid");
-    conv_first_kernel<<<dim3((W + 127) / 128, H, N), 256, 0, st>>>(fp);
+    if (N > 65535) return fail(MOE_ERR_INVALID, "too many planes for the conv_input grid");
+    int first_rows = 0, first_nseg = 0;
+    choose_segments(static_cast<int64_t>(N) * ((W + 127) / 128), 2 * e->sm_count, H, 8, &first_rows, &first_nseg);
+    conv_first_kernel<<<dim3((W + 127) / 128, first_nseg, N), 256, 0, st>>>(fp, first_rows);
     }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 

@@ -29,70 +29,83 @@ struct FirstParams {
   __half* out;                     // NHWC (N,H,W,64)
 };
 
-// conv_input (1 -> 64, 3x3) + PReLU  (models.py:112,118).  A block covers 128 pixels of one row: the 3 x 130 input
-// window goes through shared memory (one coalesced load per element, padImage / tile-border logic evaluated once
-// per element), then every thread computes 8 output channels of 4 consecutive pixels (8 threads = one 4-pixel
-// group, so each store instruction of a warp writes four full 128-byte pixels).  2 B read, 128 B written per pixel.
-__global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p)
+// conv_input (1 -> 64, 3x3) + PReLU  (models.py:112,118).  A block owns a 128-pixel-wide column strip of one plane
+// and walks down `seg_rows` rows with a rolling 4-row window in shared memory: one new input row (130 values,
+// padImage / tile-border logic evaluated once per element) is fetched while the current row is computed, the 72
+// weights a thread needs stay in registers for the whole walk.  Every thread computes 8 output channels of 4
+// consecutive pixels (8 threads = one 4-pixel group, so each store instruction of a warp writes four full 128-byte
+// pixels).  2 B read, 128 B written per pixel.
+__device__ __forceinline__ float first_fetch(const FirstParams& p, int n, int yy, int xx) {
+  if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) return 0.f;
+  const int sy = pad_src(p.top + yy, p.in_h, p.in_h + p.pad_h);
+  const int sx = pad_src(p.left + xx, p.in_w, p.in_w + p.pad_w);
+  return (sy >= 0 && sx >= 0) ? __half2float(p.img[n * p.plane_stride + sy * p.row_stride + sx]) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p, int seg_rows)
 {
-  __shared__ float win_s[3][132];
+  __shared__ float win_s[4][132];
   const int x0 = blockIdx.x * 128;
-  const int y = blockIdx.y;
+  const int y0 = blockIdx.y * seg_rows;
+  const int y1 = min(p.H, y0 + seg_rows);
   const int n = blockIdx.z;
-  for (int i = threadIdx.x; i < 3 * 130; i += 256) {
-    const int dy = i / 130, c = i - dy * 130;
-    const int yy = y + dy - 1, xx = x0 + c - 1;
-    float v = 0.f;
-    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-      const int sy = pad_src(p.top + yy, p.in_h, p.in_h + p.pad_h);
-      const int sx = pad_src(p.left + xx, p.in_w, p.in_w + p.pad_w);
-      if (sy >= 0 && sx >= 0) v = __half2float(p.img[n * p.plane_stride + sy * p.row_stride + sx]);
-    }
-    win_s[dy][c] = v;
+  const int t = threadIdx.x;
+  // rows y0-1, y0, y0+1 of the window
+  for (int i = t; i < 3 * 130; i += 256) {
+    const int r = i / 130, c = i - r * 130;
+    win_s[(y0 - 1 + r) & 3][c] = first_fetch(p, n, y0 - 1 + r, x0 + c - 1);
+  }
+  const int g = t & 7;
+  const int xl = (t >> 3) * 4;                     // first of this thread's 4 pixels, relative to x0
+  const int x = x0 + xl;
+  float wreg[9][8];                                // this thread's 8 output channels of every tap
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + k * 64 + g * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + k * 64 + g * 8 + 4));
+    wreg[k][0] = w0.x; wreg[k][1] = w0.y; wreg[k][2] = w0.z; wreg[k][3] = w0.w;
+    wreg[k][4] = w1.x; wreg[k][5] = w1.y; wreg[k][6] = w1.z; wreg[k][7] = w1.w;
   }
   __syncthreads();
-  const int g = threadIdx.x & 7;
-  const int xl = (threadIdx.x >> 3) * 4;           // first of this thread's 4 pixels, relative to x0
-  const int x = x0 + xl;
-  if (x >= p.W) return;
-  float win[3][6];
+  for (int y = y0; y < y1; ++y) {
+    // fetch the row two below early (its latency hides behind this row's math); stored after the compute
+    const float nxt = t < 130 ? first_fetch(p, n, y + 2, x0 + t - 1) : 0.f;
+    if (x < p.W) {
+      float win[3][6];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
+      for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 6; ++dx) win[dy][dx] = win_s[dy][xl + dx];
-  float wreg[9][8];                                // this thread's 8 output channels of every tap (L1-resident, 2.3 KB in all)
+        for (int dx = 0; dx < 6; ++dx) win[dy][dx] = win_s[(y - 1 + dy) & 3][xl + dx];
+      const size_t pix0 = (static_cast<size_t>(n) * p.H + y) * p.W + x;
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * 64 + g * 8));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + t * 64 + g * 8 + 4));
-    wreg[t][0] = w0.x; wreg[t][1] = w0.y; wreg[t][2] = w0.z; wreg[t][3] = w0.w;
-    wreg[t][4] = w1.x; wreg[t][5] = w1.y; wreg[t][6] = w1.z; wreg[t][7] = w1.w;
-  }
-  const size_t pix0 = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      for (int i = 0; i < 4; ++i) {
+        if (x + i >= p.W) break;
+        float a[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (x + i >= p.W) break;
-    float a[8];
+        for (int c = 0; c < 8; ++c) a[c] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = 0.f;
+        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) {
+            const float v = win[dy][i + dx];
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const float v = win[dy][i + dx];
+            for (int c = 0; c < 8; ++c) a[c] = fmaf(v, wreg[dy * 3 + dx][c], a[c]);
+          }
+        uint32_t w[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) a[c] = fmaf(v, wreg[dy * 3 + dx][c], a[c]);
+        for (int c = 0; c < 4; ++c) {
+          float f0 = a[2 * c], f1 = a[2 * c + 1];
+          f0 = f0 >= 0.f ? f0 : p.slope * f0;
+          f1 = f1 >= 0.f ? f1 : p.slope * f1;
+          const __half2 hv = __floats2half2_rn(f0, f1);
+          w[c] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+        reinterpret_cast<uint4*>(p.out + (pix0 + i) * 64)[g] = make_uint4(w[0], w[1], w[2], w[3]);
       }
-    uint32_t w[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float f0 = a[2 * c], f1 = a[2 * c + 1];
-      f0 = f0 >= 0.f ? f0 : p.slope * f0;
-      f1 = f1 >= 0.f ? f1 : p.slope * f1;
-      const __half2 hv = __floats2half2_rn(f0, f1);
-      w[c] = *reinterpret_cast<const uint32_t*>(&hv);
     }
-    reinterpret_cast<uint4*>(p.out + (pix0 + i) * 64)[g] = make_uint4(w[0], w[1], w[2], w[3]);
+    // row y+2 replaces row y-2 in the ring: nobody reads slot (y+2)&3 during this iteration (rows y-1..y+1 are read)
+    if (t < 130) win_s[(y + 2) & 3][t] = nxt;
+    __syncthreads();
   }
 }
 

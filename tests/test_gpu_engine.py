@@ -347,3 +347,59 @@ def test_fused_path_at_4k_tile_width(engine):
         assert (y.float() - y_simt.float()).abs().max().item() <= 1e-3
     finally:
         config.freeMemOverride = None
+
+
+@pytest.mark.parametrize('key,scale,shape', [('a2', 2, (3, 1, 1)), ('a2', 2, (1, 5, 7)), ('a4', 4, (3, 9, 3)), ('a3', 3, (2, 8, 130)), ('a2', 2, (4, 131, 9))])
+def test_degenerate_and_ragged_shapes(engine, key, scale, shape):
+    """smallest inputs the reference accepts (a single tile padded to 8 by reflect-then-zero padImage), widths just
+    over one 128-px strip, plane counts 1..4 — against the oracle with the engine's rounding points"""
+    from oracle import net as N, tiling as T
+    from moephoto_b200 import imageProcess as IP
+    from moephoto_b200.config import config
+    opt = _sr_opt(key, scale, ram=int(4e9))
+    try:
+        x = torch.rand(shape, generator=torch.Generator().manual_seed(sum(shape))).half()
+        y = IP.doCrop(opt, x.cuda())
+        assert tuple(y.shape) == (shape[0], shape[1] * scale, shape[2] * scale)
+        sd = H.load_weights(key)
+        plan = T.make_plan(shape, int(4e9), opt.ramCoef, opt.padding, scale, 8, 0)
+        assert plan.tiles == opt.plan.tiles and (plan.pad_h, plan.pad_w) == (opt.plan.pad_h, opt.plan.pad_w)
+        want = T.do_crop(lambda a: N.forward(sd, a, mode='f16io'), x.float().numpy(), plan, np.float16).astype(np.float32)
+        d = np.abs(y.float().cpu().numpy() - want)
+        assert d.max() <= 2e-3 and (d > 1e-3).mean() < 2e-3          # white-noise input: up to two fp16 ulps, see test_bare_network_call
+    finally:
+        config.freeMemOverride = None
+
+
+def test_full_size_4k_a4_bench_workload(engine):
+    """BASELINE configs[2] at full size (3840x2160 -> 15360x8640, a4, the reference's 4-strip auto plan):
+      * 8-way row-band sharding (what 8 GPUs compute) is bit-identical to the single run;
+      * a 96x96 crop taken well inside one reference tile and run on its own reproduces the full frame bit for bit in
+        its interior (receptive field 16 LR px), and that crop matches the oracle — parity carried to the full size."""
+    from oracle import net as N
+    from moephoto_b200 import imageProcess as IP, parallel as PAR
+    from moephoto_b200.config import config
+    import bench
+    opt = _sr_opt('a4', 4)
+    try:
+        x = IP.toTorch(8)(bench.synthetic_frame(2160, 3840, 0))
+        y = IP.doCrop(opt, x)
+        assert len(opt.plan.tiles) == 4 and tuple(y.shape) == (3, 8640, 15360)
+        assert [(t[0], t[1], t[2], t[3]) for t in opt.plan.tiles] == [(0, 2160, 0, 968), (0, 2160, 963, 1931), (0, 2160, 1921, 2889), (0, 2160, 2880, 3840)]
+        assert torch.isfinite(y).all()
+        out = torch.empty_like(y)
+        for rank in range(8):
+            lo, hi = PAR.band_rows(2160, 4, 8, rank)
+            IP.run_plan(opt.modelCached, x, opt.plan, out, rows=(lo, hi))
+        assert torch.equal(out, y)
+        del out
+        # crop inside tile 1 (columns 963..1931), away from every seam
+        cy, cx, s = 1000, 1400, 96
+        crop = x[:, cy:cy + s, cx:cx + s].contiguous()
+        yc = opt(crop.unsqueeze(1))[:, 0]                               # bare network on the crop, zero padded at its border
+        m = 16
+        assert torch.equal(yc[:, 4 * m:4 * (s - m), 4 * m:4 * (s - m)], y[:, 4 * (cy + m):4 * (cy + s - m), 4 * (cx + m):4 * (cx + s - m)])
+        want = N.forward(H.load_weights('a4'), crop.float().cpu().numpy()[:, None], mode='f16io')[:, 0]
+        assert np.abs(yc.float().cpu().numpy() - want).max() <= 1e-3
+    finally:
+        config.freeMemOverride = None
