@@ -200,6 +200,16 @@ def main():
   local = int(os.environ.get('LOCAL_RANK', '0'))
   if args.impl == 'reference':
     return run_reference(args, rank)
+  # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on fd 1 when the first
+  # communicator is created) are sent to stderr for the duration of the run
+  sys.stdout.flush()
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+
+  def emit(line):
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
 
   import torch
   import torch.distributed as dist
@@ -341,7 +351,7 @@ def main():
     sec = min(ts)
     line['cpu_baseline'] = {'value': (CPU_SAMPLE * SCALE) ** 2 / 1e6 / sec, 'unit': 'MPix/s', 'cores': threads, 'kind': 'port',
                             'sample': 'a4 on a %dx%d crop (1 warm-up, best of 3), oracle port with PyTorch CPU conv2d, fp32' % (CPU_SAMPLE, CPU_SAMPLE)}
-  print(json.dumps(line))
+  emit(line)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
