@@ -53,7 +53,8 @@ typedef enum {
   MOE_ARCH_NET2X = 2,        /* models.Net2x : a2 / p2 */
   MOE_ARCH_NET3X = 3,        /* models.Net3x : a3 / p3 */
   MOE_ARCH_NET4X = 4,        /* models.Net4x : a4 / p4 */
-  MOE_ARCH_NETDN = 1         /* models.NetDN : dn_lite5/10/15 */
+  MOE_ARCH_NETDN = 1,        /* models.NetDN : dn_lite5/10/15 */
+  MOE_ARCH_LITE = 5          /* MoeNet_lite2.Net : lite2 / lite4 / lite8 (runSR.py:21-23) */
 } MoeArch;
 
 typedef struct MoeEngine MoeEngine;

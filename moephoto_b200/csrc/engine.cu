@@ -85,8 +85,10 @@ struct MoeModel {
   const float* first_w = nullptr;
   float scalars[32] = {0};
   const uint8_t* trunk_img[13] = {nullptr};
-  const uint8_t* up_img[4] = {nullptr, nullptr, nullptr, nullptr};
-  const float* up_bias[4] = {nullptr, nullptr, nullptr, nullptr};
+  const uint8_t* up_img[8] = {nullptr};     // [4*branch + stage]
+  const float* up_bias[8] = {nullptr};
+  const float* frm[3] = {nullptr, nullptr, nullptr};   // MoeNet_lite2's FRM gates
+  float* d_frm_ws = nullptr;                 // partial sums + gates of the FRM reduction
   const float* head_w[2] = {nullptr, nullptr};
   uint8_t* d_head_img = nullptr;   // [2][16 rows][128 B] swizzled fp16 image of the two head filters (head_tc.cuh)
 };
@@ -364,10 +366,16 @@ TileGeom tile_geom(const MoePlan& pl, const MoeTile& t, int row_lo, int row_hi) 
   return g;
 }
 
+// workspace of one tile in units of (planes x h x w x 128 B): A, T, M, C, then for PixelShuffle(2) nets the shared
+// stage buffers S1 (4 units, if >= 2 stages) and S2 (16 units, if 3 stages) and the final region — two 4^n_up-unit
+// tensors (unfused) or the P array (fused, smaller); PixelShuffle(3): two 9-unit tensors.
+size_t stage_units(const MoeModel* m) { return (m->n_up >= 2 ? 4 : 0) + (m->n_up >= 3 ? 16 : 0); }
 size_t tile_units(const MoeModel* m) {
-  if (m->n_up == 0) return 3;
-  if (m->n_up == 1) return 3 + 2 * static_cast<size_t>(m->r) * m->r;
-  return 3 + 4 + 32;
+  if (m->n_up == 0) return 4;
+  if (m->r == 3) return 4 + 2 * 9;
+  size_t fin = 2;
+  for (int i = 0; i < m->n_up; ++i) fin *= 4;
+  return 4 + stage_units(m) + fin;
 }
 
 int validate_plan(const MoeModel* m, const MoePlan* pl, int planes, int row_lo, int row_hi) {
@@ -482,18 +490,21 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
   memcpy(&h, blob, sizeof h);
   if (h.magic != kBlobMagic || h.version != kBlobVersion) return fail(MOE_ERR_INVALID, "not a moephoto_b200 weight blob");
   if (static_cast<int>(h.arch) != arch) return fail(MOE_ERR_INVALID, "blob is arch %u, asked for %d", h.arch, arch);
-  if (h.n_up > 2 || (h.n_up && h.r != 2 && h.r != 3) || (h.n_up == 2 && h.r != 2)) return fail(MOE_ERR_INVALID, "unsupported upsample layout");
+  if (h.n_up > 3 || (h.n_up && h.r != 2 && h.r != 3) || (h.n_up >= 2 && h.r != 2)) return fail(MOE_ERR_INVALID, "unsupported upsample layout");
+  if (arch != MOE_ARCH_NET2X && arch != MOE_ARCH_NET3X && arch != MOE_ARCH_NET4X && arch != MOE_ARCH_NETDN && arch != MOE_ARCH_LITE)
+    return fail(MOE_ERR_INVALID, "unknown architecture %d", arch);
   if (nbytes < sizeof h + h.n_sections * sizeof(BlobEntry)) return fail(MOE_ERR_INVALID, "truncated directory");
   Guard g(e->device);
   if (!g.ok) return fail(MOE_ERR_CUDA, "cudaSetDevice failed");
   MoeModel* m = new MoeModel();
   m->e = e; m->arch = arch; m->feat = h.feat; m->n_up = h.n_up; m->r = h.r;
-  m->scale = h.n_up == 0 ? 1 : (h.n_up == 1 ? static_cast<int>(h.r) : 4);
+  m->scale = 1;
+  for (uint32_t i = 0; i < h.n_up; ++i) m->scale *= static_cast<int>(h.r);
   if (cudaMalloc(&m->d_blob, nbytes) != cudaSuccess) { delete m; cudaGetLastError(); return fail(MOE_ERR_NOMEM, "cudaMalloc(%zu) for weights failed", nbytes); }
   if (cudaMemcpy(m->d_blob, blob, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_CUDA, "weight upload failed"); }
   const uint8_t* hb = static_cast<const uint8_t*>(blob);
   bool have_scalars = false;
-  int n_trunk = 0, n_head = 0, n_up_img = 0, n_up_bias = 0;
+  int n_trunk = 0, n_head = 0, n_up_img = 0, n_up_bias = 0, n_frm = 0;
   const size_t n_chunks = h.n_up ? static_cast<size_t>(h.r) * h.r : 0;
   for (uint32_t i = 0; i < h.n_sections; ++i) {
     BlobEntry en;
@@ -504,17 +515,25 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
       case SEC_FIRST_W: bad |= en.nbytes != 9 * 64 * 4; m->first_w = reinterpret_cast<const float*>(dp); break;
       case SEC_SCALARS: bad |= en.nbytes != sizeof m->scalars; if (!bad) { memcpy(m->scalars, hb + en.offset, sizeof m->scalars); have_scalars = true; } break;
       case SEC_TRUNK_IMG: bad |= en.index >= 13 || en.nbytes != kChunkImgBytes; if (!bad) { m->trunk_img[en.index] = dp; ++n_trunk; } break;
-      case SEC_UP_IMG: bad |= en.index >= 4 || en.nbytes != n_chunks * kChunkImgBytes; if (!bad) { m->up_img[en.index] = dp; ++n_up_img; } break;
-      case SEC_UP_BIAS: bad |= en.index >= 4 || en.nbytes != n_chunks * 64 * 4; if (!bad) { m->up_bias[en.index] = reinterpret_cast<const float*>(dp); ++n_up_bias; } break;
+      case SEC_UP_IMG: bad |= en.index >= 8 || en.nbytes != n_chunks * kChunkImgBytes; if (!bad) { m->up_img[en.index] = dp; ++n_up_img; } break;
+      case SEC_UP_BIAS: bad |= en.index >= 8 || en.nbytes != n_chunks * 64 * 4; if (!bad) { m->up_bias[en.index] = reinterpret_cast<const float*>(dp); ++n_up_bias; } break;
+      case SEC_FRM: bad |= en.index >= 3 || en.nbytes != 516 * 4; if (!bad) { m->frm[en.index] = reinterpret_cast<const float*>(dp); ++n_frm; } break;
       case SEC_HEAD_W: bad |= en.index >= 2 || en.nbytes != 9 * 64 * 4; if (!bad) { m->head_w[en.index] = reinterpret_cast<const float*>(dp); ++n_head; } break;
       default: bad = true;
     }
     if (bad) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "bad blob section %u (kind %u index %u)", i, en.kind, en.index); }
   }
   const int want_up = 2 * static_cast<int>(h.n_up);
-  bool complete = m->first_w && have_scalars && n_trunk == 13 && n_head == 2 && n_up_img == want_up && n_up_bias == want_up;
+  const bool lite = arch == MOE_ARCH_LITE;
+  bool complete = m->first_w && have_scalars && n_trunk == (lite ? 7 : 13) && n_head == 2 && n_up_img == want_up && n_up_bias == want_up &&
+                  n_frm == (lite ? 3 : 0);
+  for (int l = 0; l < (lite ? 7 : 13) && complete; ++l) complete = m->trunk_img[l] != nullptr;
   for (int b = 0; b < 2 && complete; ++b)
-    for (uint32_t s = 0; s < h.n_up; ++s) complete = m->up_img[2 * b + s] && m->up_bias[2 * b + s];
+    for (uint32_t s = 0; s < h.n_up && complete; ++s) complete = m->up_img[4 * b + s] && m->up_bias[4 * b + s];
+  if (complete && lite && cudaMalloc(&m->d_frm_ws, (static_cast<size_t>(kFrmBlocks) + 1) * 64 * 4 * 256) != cudaSuccess) {   // up to 256 planes
+    cudaGetLastError(); cudaFree(m->d_blob); delete m;
+    return fail(MOE_ERR_NOMEM, "FRM workspace allocation failed");
+  }
   if (!complete) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "blob is missing sections"); }
   {
     // head filters as a K-major SWIZZLE_128B B operand: row = tap (9 of 16 used), 64 input channels
@@ -541,6 +560,7 @@ void moe_model_free(MoeModel* m)
   Guard g(m->e->device);
   if (m->d_blob) cudaFree(m->d_blob);
   if (m->d_head_img) cudaFree(m->d_head_img);
+  if (m->d_frm_ws) cudaFree(m->d_frm_ws);
   delete m;
 }
 
@@ -551,8 +571,9 @@ size_t moe_plan_workspace_bytes(const MoeModel* m, int planes, const MoePlan* pl
   if (validate_plan(m, plan, planes, row_lo, row_hi) != MOE_OK) return 0;
   size_t worst = 0;
   for (int i = 0; i < plan->n_tiles; ++i) {
-    const TileGeom g = tile_geom(*plan, plan->tiles[i], row_lo, row_hi);
+    TileGeom g = tile_geom(*plan, plan->tiles[i], row_lo, row_hi);
     if (!g.active) continue;
+    if (m->arch == MOE_ARCH_LITE) g.H = plan->tiles[i].bottom - plan->tiles[i].top;
     const size_t unit = align_up(static_cast<size_t>(planes) * g.H * g.W * 128, 1024);
     worst = std::max(worst, unit * tile_units(m));
   }
@@ -578,14 +599,16 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
 
   for (int ti = 0; ti < plan->n_tiles; ++ti) {
     const MoeTile& t = plan->tiles[ti];
-    const TileGeom g = tile_geom(*plan, t, row_lo, row_hi);
+    TileGeom g = tile_geom(*plan, t, row_lo, row_hi);
     if (!g.active) continue;
+    if (m->arch == MOE_ARCH_LITE) { g.c0 = 0; g.c1 = t.bottom - t.top; g.H = g.c1; }   // FRM averages over the WHOLE tile: no row window
     const int H = g.H, W = g.W;
     const size_t unit = align_up(static_cast<size_t>(N) * H * W * 128, 1024);
     __half* bufA = reinterpret_cast<__half*>(ws);              // `out`  = PReLU(conv_input(x))
     __half* bufT = reinterpret_cast<__half*>(ws + unit);       // trunk  t
-    __half* bufM = reinterpret_cast<__half*>(ws + 2 * unit);   // ARSB mid
-    uint8_t* up0 = ws + 3 * unit;
+    __half* bufM = reinterpret_cast<__half*>(ws + 2 * unit);   // ARSB / LB mid
+    __half* bufC = reinterpret_cast<__half*>(ws + 3 * unit);   // LB conv_2 output before the FRM gate (MoeNet_lite2)
+    uint8_t* up0 = ws + 4 * unit;
 
     // conv_input + PReLU                                                       models.py:118
     FirstParams fp{};
@@ -603,51 +626,68 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 
-    // conv_input2, then six ARSBs: t += scale * conv_2(PReLU(conv_1(t)))        models.py:119, 76-80
-    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
-    for (int b = 0; b < 6; ++b) {
-      const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
-      if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
-      if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
+    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;   // conv_input2
+    if (m->arch == MOE_ARCH_LITE) {
+      // three LB blocks: t = FRM(conv_2(PReLU(conv_1(t)))) + t                  MoeNet_lite2.py:7-20, models.py:270-287
+      if (N > 256) return fail(MOE_ERR_INVALID, "MoeNet_lite2: more than 256 planes per call");
+      float* partial = m->d_frm_ws;
+      float* gate = m->d_frm_ws + static_cast<size_t>(kFrmBlocks) * 64 * 256;
+      const int64_t px = static_cast<int64_t>(H) * W;
+      for (int b = 0; b < 3; ++b) {
+        const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
+        if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, bufM, bufC, nullptr, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
+        frm_partial_kernel<<<dim3(kFrmBlocks, N), 256, 0, st>>>(bufC, partial, px);
+        if ((rc = check_launch(e, "frm_partial_kernel")) != MOE_OK) return rc;
+        frm_gate_kernel<<<N, 64, 0, st>>>(partial, m->frm[b], gate, 1.0f / static_cast<float>(px));
+        if ((rc = check_launch(e, "frm_gate_kernel")) != MOE_OK) return rc;
+        frm_apply_kernel<<<grid_for(px * N * 8, 256, e->sm_count), 256, 0, st>>>(bufC, bufT, gate, px, N);
+        if ((rc = check_launch(e, "frm_apply_kernel")) != MOE_OK) return rc;
+      }
+    } else {
+      // six ARSBs: t += scale * conv_2(PReLU(conv_1(t)))                        models.py:76-80
+      for (int b = 0; b < 6; ++b) {
+        const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
+        if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
+      }
     }
 
-    // the two upsample stacks u(out) and convt_R1(t)                          models.py:29-33,125-154
+    // the two upsample stacks: branch 0 on `out`, branch 1 on the trunk           models.py:29-33,125-154; MoeNet_lite2.py:47-50
     const __half* head_in[2] = {bufA, bufT};
     const bool fuse = !e->simt && !e->no_pair && !e->no_fuse && m->n_up >= 1 && m->r == 2 && e->sm_count >= 4;
-    const size_t pbytes = align_up(static_cast<size_t>(N) * 9 * (H * sc) * (W * sc) * sizeof(float), 1024);
-    float* pbuf[2] = {nullptr, nullptr};
-    if (fuse && m->n_up == 1) {
+    float* pbuf = nullptr;
+    if (m->n_up >= 1 && m->r == 2) {
+      __half* stage_buf[2] = {reinterpret_cast<__half*>(up0), reinterpret_cast<__half*>(up0 + 4 * unit)};   // S1 (4 units), S2 (16 units)
+      uint8_t* fin = up0 + stage_units(m) * unit;
+      size_t fin_units = 1;
+      for (int i = 0; i < m->n_up; ++i) fin_units *= 4;
+      pbuf = reinterpret_cast<float*>(fin);                        // fused: branch 1 accumulates onto branch 0's P
       for (int b = 0; b < 2; ++b) {
-        pbuf[b] = reinterpret_cast<float*>(up0);                    // branch R accumulates onto branch u's P
-        if ((rc = launch_conv_head(e, st, b ? bufT : bufA, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, m->scalars[14 + 2 * b],
-                                   m->d_head_img + b * 2048, pbuf[b], b)) != MOE_OK) return rc;
+        const __half* src = b ? bufT : bufA;
+        for (int s2 = 0; s2 < m->n_up; ++s2) {
+          const int hs = H << s2, wsz = W << s2;
+          const bool last = s2 == m->n_up - 1;
+          const uint8_t* wimg = m->up_img[4 * b + s2];
+          const float* wb = m->up_bias[4 * b + s2];
+          const float slope = m->scalars[14 + 4 * b + s2];
+          if (last && fuse) {
+            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, pbuf, b)) != MOE_OK) return rc;
+          } else {
+            __half* dst = last ? reinterpret_cast<__half*>(fin + b * fin_units * unit) : stage_buf[s2];
+            if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, N, hs, wsz, 2, EPI_BIAS_PRELU, slope)) != MOE_OK) return rc;
+            src = dst;
+            if (last) head_in[b] = dst;
+          }
+        }
       }
-    } else if (fuse && m->n_up == 2) {
-      __half* s1 = reinterpret_cast<__half*>(up0);                 // 4 units, shared by both branches
-      for (int b = 0; b < 2; ++b) {
-        pbuf[b] = reinterpret_cast<float*>(up0 + 4 * unit);          // branch R accumulates onto branch u's P
-        if ((rc = launch_conv(e, st, b ? bufT : bufA, s1, nullptr, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, 2,
-                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b])) != MOE_OK) return rc;
-        if ((rc = launch_conv_head(e, st, s1, m->up_img[2 * b + 1], m->up_bias[2 * b + 1], N, 2 * H, 2 * W, m->scalars[14 + 2 * b + 1],
-                                   m->d_head_img + b * 2048, pbuf[b], b)) != MOE_OK) return rc;
-      }
-    } else if (m->n_up == 1) {
-      const size_t usz = unit * m->r * m->r;
+    } else if (m->n_up == 1) {                                     // PixelShuffle(3)
+      const size_t usz = unit * 9;
       for (int b = 0; b < 2; ++b) {
         __half* dst = reinterpret_cast<__half*>(up0 + b * usz);
-        if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, m->r,
-                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b])) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[4 * b], m->up_bias[4 * b], N, H, W, 3,
+                              EPI_BIAS_PRELU, m->scalars[14 + 4 * b])) != MOE_OK) return rc;
         head_in[b] = dst;
-      }
-    } else if (m->n_up == 2) {
-      __half* s1 = reinterpret_cast<__half*>(up0);                 // 4 units, shared by both branches
-      for (int b = 0; b < 2; ++b) {
-        __half* s2 = reinterpret_cast<__half*>(up0 + 4 * unit + b * 16 * unit);
-        if ((rc = launch_conv(e, st, b ? bufT : bufA, s1, nullptr, m->up_img[2 * b], m->up_bias[2 * b], N, H, W, 2,
-                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b])) != MOE_OK) return rc;
-        if ((rc = launch_conv(e, st, s1, s2, nullptr, m->up_img[2 * b + 1], m->up_bias[2 * b + 1], N, 2 * H, 2 * W, 2,
-                              EPI_BIAS_PRELU, m->scalars[14 + 2 * b + 1])) != MOE_OK) return rc;
-        head_in[b] = s2;
       }
     }
 
@@ -663,7 +703,7 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
     if (fuse) {
       HeadStencilParams sp{};
-      sp.g = hp; sp.pu = pbuf[0];
+      sp.g = hp; sp.pu = pbuf;
       dim3 sgrid((hp.W + 255) / 256, hp.H, N);
       if (sgrid.y > 65535u || sgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the stencil kernel grid");
       Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (36 + 2));   // bytes: one 9-float read, one fp16 write

@@ -240,6 +240,80 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(const ConvParams p)
   }
 }
 
+// ---- FRM, the feature recalibration module of MoeNet_lite2 (models.py:270-287; used by LB, MoeNet_lite2.py:15-19):
+// t <- v * sigmoid(W1 relu(W0 mean_hw(v) + b0) + b1) + t.  The mean is over the whole reference tile, so the
+// reduction is two deterministic passes (fixed chunking, fixed summation order: the result is reproducible).
+constexpr int kFrmBlocks = 512;                    // partial sums per plane
+
+// partial[n][blk][64] = sum of v[n, pixels of chunk blk, :]
+__global__ void __launch_bounds__(256) frm_partial_kernel(const __half* v, float* partial, int64_t pixels_per_plane)
+{
+  __shared__ float red[32][65];
+  const int n = blockIdx.y, blk = blockIdx.x;
+  const int64_t chunk = (pixels_per_plane + kFrmBlocks - 1) / kFrmBlocks;
+  const int64_t p0 = blk * chunk, p1 = min(pixels_per_plane, p0 + chunk);
+  const int g = threadIdx.x & 7, lane_px = threadIdx.x >> 3;           // 8 channel groups x 32 pixel lanes
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint4* base = reinterpret_cast<const uint4*>(v + static_cast<size_t>(n) * pixels_per_plane * 64);
+  for (int64_t px = p0 + lane_px; px < p1; px += 32) {
+    const uint4 q = __ldg(base + px * 8 + g);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); a[2 * e] += f.x; a[2 * e + 1] += f.y; }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) red[lane_px][g * 8 + c] = a[c];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+    for (int l = 0; l < 32; ++l) s += red[l][threadIdx.x];
+    partial[(static_cast<size_t>(n) * kFrmBlocks + blk) * 64 + threadIdx.x] = s;
+  }
+}
+
+// gate[n][c] = sigmoid(b1[c] + sum_j w1[c][j] * relu(b0[j] + sum_k w0[j][k] * mean[n][k]));  frm = w0[3][64], b0[4], w1[64][4], b1[64]
+__global__ void __launch_bounds__(64) frm_gate_kernel(const float* partial, const float* frm, float* gate, float inv_pixels)
+{
+  __shared__ float mean[64];
+  __shared__ float hid[4];
+  const int n = blockIdx.x, c = threadIdx.x;
+  float s = 0.f;
+  for (int b = 0; b < kFrmBlocks; ++b) s += partial[(static_cast<size_t>(n) * kFrmBlocks + b) * 64 + c];
+  mean[c] = s * inv_pixels;
+  __syncthreads();
+  if (c < 3) {
+    float h = frm[192 + c];
+    for (int k = 0; k < 64; ++k) h += frm[c * 64 + k] * mean[k];
+    hid[c] = fmaxf(h, 0.f);
+  }
+  __syncthreads();
+  const float z = frm[452 + c] + frm[196 + c * 4] * hid[0] + frm[196 + c * 4 + 1] * hid[1] + frm[196 + c * 4 + 2] * hid[2];
+  gate[n * 64 + c] = 1.f / (1.f + expf(-z));
+}
+
+// t = round16(v * gate + t), NHWC, 8 channels per thread
+__global__ void __launch_bounds__(256) frm_apply_kernel(const __half* v, __half* t, const float* gate, int64_t pixels_per_plane, int planes)
+{
+  const int64_t total = pixels_per_plane * planes * 8;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 7);
+    const int n = static_cast<int>((i >> 3) / pixels_per_plane);
+    const uint4 qv = __ldg(reinterpret_cast<const uint4*>(v) + i);
+    uint4 qt = reinterpret_cast<const uint4*>(t)[i];
+    const __half2* hv = reinterpret_cast<const __half2*>(&qv);
+    __half2* ht = reinterpret_cast<__half2*>(&qt);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + n * 64 + g * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + n * 64 + g * 8 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fv = __half22float2(hv[e]), ft = __half22float2(ht[e]);
+      ht[e] = __floats2half2_rn(__fadd_rn(__fmul_rn(fv.x, gg[2 * e]), ft.x), __fadd_rn(__fmul_rn(fv.y, gg[2 * e + 1]), ft.y));
+    }
+    reinterpret_cast<uint4*>(t)[i] = qt;
+  }
+}
+
 // y = s*y + (1-s)*x, every op rounded to fp16 (strengthOp, imageProcess.py:562)
 __global__ void axpby_f16_kernel(__half* y, const __half* x, float s, float t, size_t count)
 {

@@ -1,4 +1,4 @@
-"""install(): route MoePhoto's a*/p*/dn_lite* models through the engine inside an existing MoePhoto
+"""install(): route MoePhoto's a*/p*/lite*/dn_lite* models through the engine inside an existing MoePhoto
 process, leaving every other model on the stock code.  Call it once, before `procedure` is imported
 (e.g. at the top of python/MoePhoto.py).  It patches three names the step-pipeline builder reads:
   runSR.getOpt / runSR.sr          procedure.py:171, :72

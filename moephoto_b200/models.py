@@ -25,3 +25,10 @@ class Net4x(_Arch):      # models.py:145-154
 
 class NetDN(_Arch):      # models.py:158-164
   arch, filters, scale = _w.ARCH_NETDN, 48, 1
+
+
+class LiteNet(_Arch):    # MoeNet_lite2.Net (MoeNet_lite2.py:22-54); `upscale` = 2, 4 or 8
+  arch, filters = _w.ARCH_LITE, 48
+
+  def __init__(self, upscale=2):
+    self.scale = upscale

@@ -15,9 +15,9 @@ Checkpoint key names: models.py:16-19 (initParameters), SURVEY.md §8a N6.
 import struct
 import numpy as np
 
-ARCH_NETDN, ARCH_NET2X, ARCH_NET3X, ARCH_NET4X = 1, 2, 3, 4
-MAGIC, VERSION = 0x42454F4D, 1
-SEC_FIRST_W, SEC_SCALARS, SEC_TRUNK_IMG, SEC_UP_IMG, SEC_UP_BIAS, SEC_HEAD_W = 1, 2, 3, 4, 5, 6
+ARCH_NETDN, ARCH_NET2X, ARCH_NET3X, ARCH_NET4X, ARCH_LITE = 1, 2, 3, 4, 5
+MAGIC, VERSION = 0x42454F4D, 2
+SEC_FIRST_W, SEC_SCALARS, SEC_TRUNK_IMG, SEC_UP_IMG, SEC_UP_BIAS, SEC_HEAD_W, SEC_FRM = 1, 2, 3, 4, 5, 6, 7
 
 
 def _np(v):
@@ -32,6 +32,8 @@ def _h(v):
 
 
 def detect_arch(sd):
+  if 'convt_F11.conv_1.weight' in sd:
+    return ARCH_LITE                      # MoeNet_lite2.Net (MoeNet_lite2.py:22-54)
   f = int(sd['conv_input.weight'].shape[0])
   if f == 48 and 'u.weight' in sd:
     return ARCH_NETDN
@@ -60,9 +62,76 @@ def conv_image(w16):
   return np.ascontiguousarray(img).view(np.uint8).reshape(-1)
 
 
+def _center(w16):
+  """(Cout,Cin,1,1) -> (Cout,Cin,3,3) with the 1x1 filter on the centre tap: a 1x1 convolution run by the 3x3 kernels"""
+  full = np.zeros(w16.shape[:2] + (3, 3), dtype=np.float16)
+  full[:, :, 1, 1] = w16[:, :, 0, 0]
+  return full
+
+
+def _finish(arch, feat, n_up, r, sections):
+  head_bytes = 32 + 24 * len(sections)
+  off = -(-head_bytes // 256) * 256
+  directory, payload = b'', b''
+  for kind, index, data in sections:
+    directory += struct.pack('<IIQQ', kind, index, off + len(payload), len(data))
+    payload += data + b'\0' * (-len(data) % 256)
+  header = struct.pack('<8I', MAGIC, VERSION, arch, feat, n_up, r, len(sections), 0)
+  blob = header + directory
+  blob += b'\0' * (off - len(blob)) + payload
+  return arch, blob
+
+
+def pack_lite(sd):
+  """MoeNet_lite2.Net: 1x1 convolutions ride the 3x3 kernels as centre-tap filters; 48 channels zero-padded to 64;
+  branch 0 = `uim` (on `out`, head convt_I1), branch 1 = `ures` (on the trunk, head convt_R1) — the same roles as
+  `u` / `convt_R1` of MyNet; FRM gates (models.py:270-287) go to their own sections."""
+  feat = 48
+  n_up = len([k for k in sd if k.startswith('ures.') and k.endswith('.0.weight')])
+  sections = []
+  first = np.zeros((9, 64), dtype=np.float32)
+  first[4, :feat] = _h(sd['conv_input.weight']).astype(np.float32).reshape(feat)
+  sections.append((SEC_FIRST_W, 0, first.tobytes()))
+  scalars = np.zeros(32, dtype=np.float32)
+  scalars[0] = _h(sd['relu.weight']).astype(np.float32).reshape(-1)[0]
+  sections.append((SEC_TRUNK_IMG, 0, conv_image(_center(_h(sd['conv_input2.weight']))).tobytes()))
+  for b, name in enumerate(('convt_F11', 'convt_F12', 'convt_F13')):
+    sections.append((SEC_TRUNK_IMG, 1 + 2 * b, conv_image(_h(sd[name + '.conv_1.weight'])).tobytes()))
+    sections.append((SEC_TRUNK_IMG, 2 + 2 * b, conv_image(_h(sd[name + '.conv_2.weight'])).tobytes()))
+    scalars[1 + 1 + 2 * b] = _h(sd[name + '.relu.weight']).astype(np.float32).reshape(-1)[0]
+    frm = np.zeros(3 * 64 + 4 + 64 * 4 + 64, dtype=np.float32)      # w0[3][64], b0[4], w1[64][4], b1[64]
+    frm[:192].reshape(3, 64)[:, :feat] = _h(sd[name + '.se.conv_du.0.weight']).astype(np.float32).reshape(3, feat)
+    frm[192:195] = _h(sd[name + '.se.conv_du.0.bias']).astype(np.float32)
+    frm[196:452].reshape(64, 4)[:feat, :3] = _h(sd[name + '.se.conv_du.2.weight']).astype(np.float32).reshape(feat, 3)
+    frm[452:452 + feat] = _h(sd[name + '.se.conv_du.2.bias']).astype(np.float32)
+    sections.append((SEC_FRM, b, frm.tobytes()))
+  for bi, (name, head) in enumerate((('uim', 'convt_I1'), ('ures', 'convt_R1'))):
+    for st in range(n_up):
+      w = _center(_h(sd['%s.%d.0.weight' % (name, st)]))            # (192, 48, 3, 3)
+      bias = _h(sd['%s.%d.0.bias' % (name, st)]).astype(np.float32)
+      imgs, bs = [], []
+      for i in range(2):
+        for j in range(2):
+          sel = np.arange(feat) * 4 + i * 2 + j
+          imgs.append(conv_image(w[sel]))
+          bq = np.zeros(64, dtype=np.float32)
+          bq[:feat] = bias[sel]
+          bs.append(bq)
+      sections.append((SEC_UP_IMG, 4 * bi + st, np.concatenate(imgs).tobytes()))
+      sections.append((SEC_UP_BIAS, 4 * bi + st, np.stack(bs).tobytes()))
+      scalars[14 + 4 * bi + st] = _h(sd['%s.%d.2.weight' % (name, st)]).astype(np.float32).reshape(-1)[0]
+    hw = np.zeros((9, 64), dtype=np.float32)
+    hw[4, :feat] = _h(sd[head + '.weight']).astype(np.float32).reshape(feat)
+    sections.append((SEC_HEAD_W, bi, hw.tobytes()))
+  sections.append((SEC_SCALARS, 0, scalars.tobytes()))
+  return _finish(ARCH_LITE, feat, n_up, 2, sections)
+
+
 def pack(sd):
   """sd: checkpoint state dict (torch tensors or numpy arrays).  Returns (arch, bytes)."""
   arch = detect_arch(sd)
+  if arch == ARCH_LITE:
+    return pack_lite(sd)
   feat = int(sd['conv_input.weight'].shape[0])
   n_up, r = {ARCH_NETDN: (0, 0), ARCH_NET2X: (1, 2), ARCH_NET3X: (1, 3), ARCH_NET4X: (2, 2)}[arch]
   sections = []   # (kind, index, bytes)
@@ -91,22 +160,13 @@ def pack(sd):
           sel = np.arange(64) * r * r + i * r + j            # PixelShuffle: channel c*r*r+i*r+j -> (c, i, j)
           imgs.append(conv_image(w[sel]))
           bs.append(bias[sel])
-      sections.append((SEC_UP_IMG, 2 * bi + s, np.concatenate(imgs).tobytes()))
-      sections.append((SEC_UP_BIAS, 2 * bi + s, np.stack(bs).astype(np.float32).tobytes()))
-      scalars[14 + 2 * bi + s] = _h(sd['%s.%d.2.weight' % (name, s)]).astype(np.float32).reshape(-1)[0]
+      sections.append((SEC_UP_IMG, 4 * bi + s, np.concatenate(imgs).tobytes()))
+      sections.append((SEC_UP_BIAS, 4 * bi + s, np.stack(bs).astype(np.float32).tobytes()))
+      scalars[14 + 4 * bi + s] = _h(sd['%s.%d.2.weight' % (name, s)]).astype(np.float32).reshape(-1)[0]
     hk = ('%s.%d.weight' % (name, n_up)) if n_up else (name + '.weight')
     head = np.zeros((9, 64), dtype=np.float32)
     head[:, :feat] = _h(sd[hk]).astype(np.float32).reshape(feat, 9).T   # (1,F,3,3) -> [tap][cin]
     sections.append((SEC_HEAD_W, bi, head.tobytes()))
   sections.append((SEC_SCALARS, 0, scalars.tobytes()))
 
-  head_bytes = 32 + 24 * len(sections)
-  off = -(-head_bytes // 256) * 256
-  directory, payload = b'', b''
-  for kind, index, data in sections:
-    directory += struct.pack('<IIQQ', kind, index, off + len(payload), len(data))
-    payload += data + b'\0' * (-len(data) % 256)
-  header = struct.pack('<8I', MAGIC, VERSION, arch, feat, n_up, r, len(sections), 0)
-  blob = header + directory
-  blob += b'\0' * (off - len(blob)) + payload
-  return arch, blob
+  return _finish(arch, feat, n_up, r, sections)

@@ -87,10 +87,13 @@ ARCH = {
   'net3x': (64, [3]),      # models.py:135-143
   'net4x': (64, [2, 2]),   # models.py:145-154
   'netdn': (48, []),       # models.py:158-164
+  'lite': (48, None),      # MoeNet_lite2.py:22-54, upscale 2 / 4 / 8 = 1 / 2 / 3 PixelShuffle(2) stages
 }
 
 
 def arch_of_state_dict(sd):
+  if 'convt_F11.conv_1.weight' in sd:
+    return 'lite'
   f = sd['conv_input.weight'].shape[0]
   if f == 48:
     return 'netdn'
@@ -103,10 +106,48 @@ def to_numpy_state(sd):
   return {k: (v.detach().cpu().numpy() if hasattr(v, 'detach') else np.asarray(v)).astype(np.float32) for k, v in sd.items()}
 
 
+def conv1x1(x, w, b=None):
+  """x (N,Cin,H,W), w (Cout,Cin,1,1) -> (N,Cout,H,W): out[n,co,y,x] = b[co] + sum_ci w[co,ci] in[n,ci,y,x]"""
+  y = np.einsum('oc,nchw->nohw', np.asarray(w, dtype=np.float32).reshape(w.shape[0], w.shape[1]), np.asarray(x, dtype=np.float32), optimize=True)
+  return (y if b is None else y + np.asarray(b, dtype=np.float32)[None, :, None, None]).astype(np.float32)
+
+
+def forward_lite(sd, x, mode='fp32', backend='c'):
+  """MoeNet_lite2.Net.forward (MoeNet_lite2.py:42-54) with LB (:7-20) and FRM (models.py:270-287):
+  out = PReLU(conv1x1(x)); t = conv1x1(out); three times t = FRM(conv3x3(PReLU(conv3x3(t)))) + t with
+  FRM(v) = v * sigmoid(W1 relu(W0 mean_hw(v) + b0) + b1); res = ures(t), im = uim(out) (each stage:
+  PReLU(PixelShuffle2(conv1x1 + bias))); y = conv1x1(res) + conv1x1(im).
+  mode 'f16io' has the CUDA engine's rounding points: every stored tensor fp16, the FRM mean / gate in fp32."""
+  q = _q16 if mode == 'f16io' else (lambda a: a)
+  W = (lambda k: _q16(sd[k])) if mode == 'f16io' else (lambda k: sd[k])
+  S = lambda k: np.float32(W(k).reshape(-1)[0])
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  out = q(prelu(conv1x1(x, W('conv_input.weight')), S('relu.weight')))
+  t = q(conv1x1(out, W('conv_input2.weight')))
+  for name in ('convt_F11', 'convt_F12', 'convt_F13'):
+    mid = q(prelu(conv3x3(t, W(name + '.conv_1.weight'), None, backend), S(name + '.relu.weight')))
+    v = q(conv3x3(mid, W(name + '.conv_2.weight'), None, backend))
+    m = v.mean(axis=(2, 3), dtype=np.float32)                                                   # (N,48)
+    hid = np.maximum(m @ W(name + '.se.conv_du.0.weight').reshape(3, 48).T + W(name + '.se.conv_du.0.bias'), 0)
+    gate = 1.0 / (1.0 + np.exp(-(hid @ W(name + '.se.conv_du.2.weight').reshape(48, 3).T + W(name + '.se.conv_du.2.bias'))))
+    t = q(v * gate.astype(np.float32)[:, :, None, None] + t)
+  stages = len([k for k in sd if k.startswith('ures.') and k.endswith('.0.weight')])
+
+  def branch(a, name):
+    for j in range(stages):
+      a = conv1x1(a, W('%s.%d.0.weight' % (name, j)), W('%s.%d.0.bias' % (name, j)))
+      a = q(prelu(pixel_shuffle(a, 2), S('%s.%d.2.weight' % (name, j))))
+    return a
+  y = conv1x1(branch(t, 'ures'), W('convt_R1.weight')) + conv1x1(branch(out, 'uim'), W('convt_I1.weight'))
+  return q(y)
+
+
 def forward(sd, x, mode='fp32', backend='c'):
   """x: (N,1,h,w) float32 (values already representable in fp16 for mode='f16io').
   Returns (N,1,s*h,s*w) float32 — the last element of MyNet.forward's list (imageProcess.py:391-395)."""
   arch = arch_of_state_dict(sd)
+  if arch == 'lite':
+    return forward_lite(sd, x, mode, backend)
   _, ups = ARCH[arch]
   q = _q16 if mode == 'f16io' else (lambda a: a)
   W = (lambda k: _q16(sd[k])) if mode == 'f16io' else (lambda k: sd[k])
@@ -140,6 +181,8 @@ def forward_torch(sd, x):
   import torch
   import torch.nn.functional as F
   T = lambda k: torch.from_numpy(np.ascontiguousarray(sd[k], dtype=np.float32))
+  if arch_of_state_dict(sd) == 'lite':
+    raise NotImplementedError('forward_torch covers the Net2x/3x/4x/NetDN baselines only')
   _, ups = ARCH[arch_of_state_dict(sd)]
   with torch.no_grad():
     x = torch.as_tensor(np.asarray(x, dtype=np.float32)) if not torch.is_tensor(x) else x

@@ -21,7 +21,8 @@ sys.path.insert(0, os.path.abspath(os.path.join(HERE, '..', '..')))
 from oracle import refharness as R   # noqa: E402
 
 CKPT = {'a2': 'a2/model_new.pth', 'a3': 'a3/model_new.pth', 'a4': 'a4/model_new.pth',
-        'dn_lite15': 'dn_lite15/model_new.pth', 'dn_lite5': 'dn_lite5/model_new.pth'}
+        'dn_lite15': 'dn_lite15/model_new.pth', 'dn_lite5': 'dn_lite5/model_new.pth',
+        'lite2': 'lite/model.pth', 'lite4': 'lite/model_4.pth', 'lite8': 'lite/model_8.pth'}
 
 
 def smooth_noise_u8(h, w, seed):
@@ -43,6 +44,10 @@ CASES = [
   ('a4_single', 'sr', 4, (40, 56), 0, 6),
   ('dn15_tiled', 'dn', 'lite15', (72, 96), 48, 7),     # pad 7
   ('dn5_single_rgba', 'dn', 'lite5', (48, 64), 0, 8),  # alpha bypass (4th plane appended below)
+  # MoeNet_lite2 (runSR.py:21-23): FRM's global mean makes the result depend on the tile, so tiled cases matter
+  ('lite2_tiled', 'sr:lite', 2, (72, 100), 48, 9),
+  ('lite4_single', 'sr:lite', 4, (40, 56), 0, 10),
+  ('lite8_single', 'sr:lite', 8, (32, 40), 0, 11),
 ]
 
 
@@ -59,8 +64,11 @@ def main():
     x = to_tensor(img)
     ram = int(ref['config'].calcFreeMem())
     ref['config'].calcFreeMem = (lambda r: (lambda *a, **k: r))(ram)   # pin the plan input we record
+    model = 'a'
+    if kind.startswith('sr:'):
+      kind, model = kind.split(':')
     if kind == 'sr':
-      y, plan, opt = R.run_sr(x, arg, crop=crop)
+      y, plan, opt = R.run_sr(x, arg, crop=crop, model=model)
     else:
       if name.endswith('rgba'):
         g = torch.Generator().manual_seed(seed + 100)
@@ -70,7 +78,7 @@ def main():
     if x.shape[0] == 4:
       out[name + '.alpha'] = x[3].numpy()
     out[name + '.ref'] = y.numpy().astype(np.float32)
-    meta[name] = dict(kind=kind, arg=arg, crop=crop, ram=ram, pad=int(opt.padding), scale=int(opt.scale),
+    meta[name] = dict(kind=kind, arg=arg, model=model, crop=crop, ram=ram, pad=int(opt.padding), scale=int(opt.scale),
                       ram_coef=float(opt.ramCoef), tiles=[[int(v) for v in t] for t in plan])
     print(name, tuple(y.shape), len(plan), 'tiles')
   out['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

@@ -35,7 +35,7 @@ def load_case(name):
   c['img'] = z[name + '.img']
   c['ref'] = z[name + '.ref']
   c['alpha'] = z[name + '.alpha'] if (name + '.alpha') in z.files else None
-  c['weights'] = WEIGHT_OF[(c['kind'], c['arg'])]
+  c['weights'] = ('lite%d' % c['arg']) if c.get('model') == 'lite' else WEIGHT_OF[(c['kind'], c['arg'])]
   return c
 
 
@@ -83,7 +83,7 @@ def run_case_engine(c):
   try:
     if c['kind'] == 'sr':
       config.crop_sr = c['crop'] if c['crop'] else 'auto'
-      opt = runSR.getOpt({'model': 'a', 'scale': c['arg']}, weights=sd)
+      opt = runSR.getOpt({'model': c.get('model', 'a'), 'scale': c['arg']}, weights=sd)
       y = runSR.sr(opt)(x)
     else:
       config.crop_dn = c['crop'] if c['crop'] else 'auto'

@@ -94,7 +94,7 @@ def test_golden_cases_through_the_reference_api(engine, name):
     assert np.array_equal(y[3], c['alpha'].astype(np.float16).astype(np.float32))
 
 
-@pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'dn15_tiled'])
+@pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'dn15_tiled', 'lite4_single'])
 def test_simt_cross_check_path_agrees_with_tensor_core_path(engine, name):
   c = H.load_case(name)
   y_tc = H.run_case_engine(c)
@@ -111,12 +111,13 @@ def _sr_opt(key, scale, crop=0, ram=int(178 * 2 ** 30 * .9)):
   from moephoto_b200.config import config
   config.freeMemOverride, config.crop_sr = ram, (crop or 'auto')
   try:
-    return runSR.getOpt({'model': 'a', 'scale': scale}, weights=H.load_weights(key))
+    return runSR.getOpt({'model': 'lite' if key.startswith('lite') else 'a', 'scale': scale}, weights=H.load_weights(key))
   finally:
     config.crop_sr = 'auto'
 
 
-@pytest.mark.parametrize('key,scale,shape,crop', [('a2', 2, (3, 300, 420), 128), ('a4', 4, (3, 200, 333), 96), ('a3', 3, (2, 150, 260), 0)])
+@pytest.mark.parametrize('key,scale,shape,crop', [('a2', 2, (3, 300, 420), 128), ('a4', 4, (3, 200, 333), 96), ('a3', 3, (2, 150, 260), 0),
+                                                  ('lite4', 4, (3, 120, 200), 64)])
 def test_row_band_sharding_is_bit_exact(engine, key, scale, shape, crop):
   """moe_run_plan's row window (what each GPU of a multi-GPU run computes) reproduces the full run exactly"""
   from moephoto_b200 import imageProcess as IP, parallel as PAR
@@ -311,7 +312,7 @@ def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
 
 
 @pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True)])
-@pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled'])
+@pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'lite2_tiled', 'lite8_single'])
 def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags):
     """the A/B switches keep the single-CTA conv kernel, the unfused CTA-pair kernel and head_tc_kernel alive;
     each variant is held to the same tolerance as the default path (CTA pairs + fused head)"""
@@ -349,7 +350,8 @@ def test_fused_path_at_4k_tile_width(engine):
         config.freeMemOverride = None
 
 
-@pytest.mark.parametrize('key,scale,shape', [('a2', 2, (3, 1, 1)), ('a2', 2, (1, 5, 7)), ('a4', 4, (3, 9, 3)), ('a3', 3, (2, 8, 130)), ('a2', 2, (4, 131, 9))])
+@pytest.mark.parametrize('key,scale,shape', [('a2', 2, (3, 1, 1)), ('a2', 2, (1, 5, 7)), ('a4', 4, (3, 9, 3)), ('a3', 3, (2, 8, 130)), ('a2', 2, (4, 131, 9)),
+                                             ('lite2', 2, (3, 3, 5)), ('lite8', 8, (1, 9, 131))])
 def test_degenerate_and_ragged_shapes(engine, key, scale, shape):
     """smallest inputs the reference accepts (a single tile padded to 8 by reflect-then-zero padImage), widths just
     over one 128-px strip, plane counts 1..4 — against the oracle with the engine's rounding points"""

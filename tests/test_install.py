@@ -33,10 +33,10 @@ def test_install_routes_engine_models_and_falls_through_for_the_rest(monkeypatch
                                     maxGraphicMemoryUsage=0)
         assert inst.install(cfg) is True
         assert ref['runSR'].getOpt({'model': 'a', 'scale': 4}) == 'ENGINE_OPT'
-        assert ref['runSR'].getOpt({'model': 'lite', 'scale': 2}) == 'STOCK_OPT'       # MoeNet_lite2 stays on the stock path
+        assert ref['runSR'].getOpt({'model': 'lite', 'scale': 2}) == 'ENGINE_OPT'      # MoeNet_lite2 is on the engine too
         assert ref['runSR'].getOpt({'model': 'gan', 'scale': 4}) == 'STOCK_OPT'
         assert ref['runDN'].getOpt({'model': 'lite15'}) == 'ENGINE_OPT'
         assert ref['runDN'].getOpt({'model': 'NAFNet_32'}) == 'STOCK_OPT'
-        assert calls == [('b_sr', 'a', 4), ('b_dn', 'lite15')] and stock == [('sr', 'lite', 2), ('sr', 'gan', 4), ('dn', 'NAFNet_32')]
+        assert calls == [('b_sr', 'a', 4), ('b_sr', 'lite', 2), ('b_dn', 'lite15')] and stock == [('sr', 'gan', 4), ('dn', 'NAFNet_32')]
     finally:
         ref['runSR'].getOpt, ref['runSR'].sr, ref['runDN'].getOpt, ref['imageProcess'].RGBFilter = saved

@@ -141,3 +141,21 @@ def test_frame_conversions_match_reference(ref):
     want = ip.toOutput(bits)(ip.toFloat(y))
     got = T.to_output(y.numpy(), bits)
     assert np.array_equal(want.astype(np.int64), got.astype(np.int64))
+
+
+@pytest.mark.parametrize('upscale,ckpt', [(2, 'lite/model.pth'), (4, 'lite/model_4.pth'), (8, 'lite/model_8.pth')])
+def test_lite_network_forward_matches_reference(ref, upscale, ckpt):
+  """MoeNet_lite2.Net (runSR.py:21-23): 1x1 convs, LB blocks with the FRM gate, PixelShuffle(2) stages"""
+  import importlib
+  lite = importlib.import_module('MoeNet_lite2')
+  sd_t = R.state_dict(ckpt)
+  model = lite.Net(upscale=upscale)
+  model.load_state_dict(sd_t)
+  model.eval()
+  x = torch.rand(2, 1, 24, 40, generator=torch.Generator().manual_seed(3))
+  with torch.no_grad():
+    want = model(x)[-1].numpy()
+  sd = N.to_numpy_state(sd_t)
+  assert N.arch_of_state_dict(sd) == 'lite'
+  got = N.forward(sd, x.numpy())
+  assert got.shape == want.shape and np.abs(got - want).max() < 2e-5

@@ -84,6 +84,6 @@ def test_getOpt_unknown_models():
   assert runSR.getOpt({'model': 'a', 'scale': 8}) is None
   with pytest.raises(KeyError):
     runDN.getOpt({'model': 'nope'})
-  assert set(runSR.mode_switch) == {'a2', 'a3', 'a4', 'p2', 'p3', 'p4'}
+  assert set(runSR.mode_switch) == {'a2', 'a3', 'a4', 'p2', 'p3', 'p4', 'lite2', 'lite4', 'lite8'}
   assert runSR.mode_switch['a4'][0] == './model/a4/model_new.pth' and abs(runSR.mode_switch['a4'][2][2] - .9 / 7029.7) < 1e-12
   assert runDN.mode_switch['lite15'][3:] == (1, 7, 8)

@@ -34,19 +34,23 @@ def test_conv_image_is_the_swizzled_k_major_layout():
   assert not back[:, 48:].any() and not back[:, :, 48:].any()
 
 
-@pytest.mark.parametrize('key,arch,n_up,r', [('a2', 2, 1, 2), ('a3', 3, 1, 3), ('a4', 4, 2, 2), ('dn_lite15', 1, 0, 0)])
+@pytest.mark.parametrize('key,arch,n_up,r', [('a2', 2, 1, 2), ('a3', 3, 1, 3), ('a4', 4, 2, 2), ('dn_lite15', 1, 0, 0), ('lite2', 5, 1, 2),
+                                             ('lite8', 5, 3, 2)])
 def test_blob_layout(key, arch, n_up, r):
   sd = H.load_weights(key)
   a, blob = W.pack(sd)
   assert a == arch
   magic, ver, arch_, feat, n_up_, r_, nsec, _ = struct.unpack_from('<8I', blob, 0)
-  assert (magic, ver, arch_, n_up_, r_) == (0x42454F4D, 1, arch, n_up, r) and feat == (48 if arch == 1 else 64)
+  assert (magic, ver, arch_, n_up_, r_) == (0x42454F4D, 2, arch, n_up, r) and feat == (48 if arch in (1, 5) else 64)
   kinds = {}
   for i in range(nsec):
     kind, index, off, nb = struct.unpack_from('<IIQQ', blob, 32 + 24 * i)
     assert off % 256 == 0 and off + nb <= len(blob)
     kinds.setdefault(kind, {})[index] = (off, nb)
-  assert len(kinds[W.SEC_TRUNK_IMG]) == 13 and len(kinds[W.SEC_HEAD_W]) == 2
+  assert len(kinds[W.SEC_TRUNK_IMG]) == (7 if arch == 5 else 13) and len(kinds[W.SEC_HEAD_W]) == 2
+  if arch == 5:
+    assert len(kinds[W.SEC_FRM]) == 3 and set(kinds[W.SEC_UP_IMG]) == {4 * b + st for b in range(2) for st in range(n_up)}
+    return
   assert len(kinds.get(W.SEC_UP_IMG, {})) == 2 * n_up
   # PixelShuffle permutation: image (i,j) of the first upsample conv holds channels c*r*r + i*r + j
   if n_up:
