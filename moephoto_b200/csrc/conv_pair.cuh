@@ -140,9 +140,10 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
               const uint64_t arow = dy == 0 ? arow0 : (dy == 1 ? arow1 : arow2);
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
+              if (p.center_only && (dy != 1 || dx != 1)) continue;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, (dy | dx | k) != 0);
+                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, p.center_only ? (k != 0) : ((dy | dx | k) != 0));
                 }
               }
             }
@@ -370,9 +371,10 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
               const uint64_t arow = dy == 0 ? arow0 : (dy == 1 ? arow1 : arow2);
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
+              if (p.center_only && (dy != 1 || dx != 1)) continue;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 256 + k * 2), idesc, (dy | dx | k) != 0);
+                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 256 + k * 2), idesc, p.center_only ? (k != 0) : ((dy | dx | k) != 0));
                 }
               }
             }

@@ -159,13 +159,13 @@ void choose_segments(int64_t base_items, int workers, int H, int min_rows, int* 
 
 // ---- one 3x3 convolution 64 -> 64*r*r ----------------------------------------------------------
 int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, const __half* skip,
-                const uint8_t* w_img, const float* bias, int N, int H, int W, int r, int epi, float param)
+                const uint8_t* w_img, const float* bias, int N, int H, int W, int r, int epi, float param, int center_only = 0)
 {
   ConvParams p{};
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
-  p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param;
-  // algorithmic FLOPs: 2 * 9 taps * Cin * Cout per input pixel (padded channels are not counted)
-  Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * 9 * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
+  p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param; p.center_only = center_only;
+  // algorithmic FLOPs: 2 * taps * Cin * Cout per input pixel (padded channels are not counted)
+  Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
   if (e->simt) {
     const int64_t threads = static_cast<int64_t>(N) * H * W * r * r * 8;
     conv3x3_simt_kernel<<<grid_for(threads, 256, e->sm_count), 256, 0, st>>>(p);
@@ -258,14 +258,14 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
 
 // ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
 int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, int N, int H, int W,
-                     float slope, const uint8_t* head_img, float* pbuf, int accumulate)
+                     float slope, const uint8_t* head_img, float* pbuf, int accumulate, int center_only = 0)
 {
   PairHeadParams hp{};
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
-  p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope;
+  p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
   hp.head_img = head_img; hp.pbuf = pbuf; hp.accumulate = accumulate;
-  Timed timed(e, st, 3, 2.0 * 9 * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
+  Timed timed(e, st, 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
   const int npairs_max = (e->sm_count / 2) & ~1;
   const int strips1 = (W + kStripW - 1) / kStripW;
   p.strips = (strips1 + 1) / 2;
@@ -626,7 +626,8 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
     }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 
-    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;   // conv_input2
+    const int one_by_one = m->arch == MOE_ARCH_LITE;            // MoeNet_lite2: conv_input2 and the upsample convs are 1x1
+    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, N, H, W, 1, EPI_PLAIN, 0.f, one_by_one)) != MOE_OK) return rc;   // conv_input2
     if (m->arch == MOE_ARCH_LITE) {
       // three LB blocks: t = FRM(conv_2(PReLU(conv_1(t)))) + t                  MoeNet_lite2.py:7-20, models.py:270-287
       if (N > 256) return fail(MOE_ERR_INVALID, "MoeNet_lite2: more than 256 planes per call");
@@ -672,10 +673,10 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
           const float* wb = m->up_bias[4 * b + s2];
           const float slope = m->scalars[14 + 4 * b + s2];
           if (last && fuse) {
-            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, pbuf, b)) != MOE_OK) return rc;
+            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, pbuf, b, one_by_one)) != MOE_OK) return rc;
           } else {
             __half* dst = last ? reinterpret_cast<__half*>(fin + b * fin_units * unit) : stage_buf[s2];
-            if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, N, hs, wsz, 2, EPI_BIAS_PRELU, slope)) != MOE_OK) return rc;
+            if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
             src = dst;
             if (last) head_in[b] = dst;
           }

@@ -267,31 +267,35 @@ def transposeShape(shape):
   return t
 
 
+def _plan_is_stale(opt, shape):
+  """the reference re-plans on first use, after 29 cached calls, or when the plane count changes — NOT when the
+  image size changes (imageProcess.py:136)"""
+  return opt.iterClip is None or opt.count > 28 or shape[0] != opt.outShape[0]
+
+
 def prepareOpt(opt, shape):
-  """imageProcess.py:133-155: the plan is cached on `opt`; re-planned on first use, after 29 cached
-  calls, or when the plane count changes (NOT when H/W change — same as the reference)."""
-  sc, pad = opt.scale, opt.padding
-  padSc = int(pad * sc)
-  if opt.iterClip is None or opt.count > 28 or shape[0] != opt.outShape[0]:
-    try:
-      freeMem = config.calcFreeMem()
-    except Exception:
-      raise MemoryError('Can not calculate free memory.')
-    opt.count = 0
-    if opt.ensemble > 0:
-      opt2 = copy(opt)
-      opt2.iterClip, opt2.padImage, opt2.unpad, *_ = prepare(transposeShape(shape), freeMem, opt2, pad, sc, opt.align, opt.cropsize)
-    opt.iterClip, opt.padImage, opt.unpad, outShape, opt.blend = prepare(shape, freeMem, opt, pad, sc, opt.align, opt.cropsize)
-    if opt.outShape is None:
-      opt.outShape = [1, *opt.oShape[1:-2], int(sc * shape[-2]), int(sc * shape[-1])] if opt.oShape else outShape
-    opt.outShape = list(opt.outShape)
-    if opt.ensemble > 0:
-      opt2.blend = opt.blend
-      opt2.outShape = transposeShape(opt.outShape)
-      opt.transposedOpt = opt2
-  else:
+  """imageProcess.py:133-155: make (or reuse) the tile plan cached on `opt`; returns (scale, seam width)."""
+  scale, pad = opt.scale, opt.padding
+  if not _plan_is_stale(opt, shape):
     opt.count += 1
-  return sc, padSc
+    return scale, int(pad * scale)
+  try:
+    free = config.calcFreeMem()
+  except Exception:
+    raise MemoryError('Can not calculate free memory.')
+  opt.count = 0
+  flipped = None
+  if opt.ensemble > 0:                         # the dihedral passes that transpose need a plan for the (W,H) image
+    flipped = copy(opt)
+    flipped.iterClip, flipped.padImage, flipped.unpad, *_ = prepare(transposeShape(shape), free, flipped, pad, scale, opt.align, opt.cropsize)
+  opt.iterClip, opt.padImage, opt.unpad, planned, opt.blend = prepare(shape, free, opt, pad, scale, opt.align, opt.cropsize)
+  if opt.outShape is None:
+    opt.outShape = planned if not opt.oShape else [1, *opt.oShape[1:-2], int(scale * shape[-2]), int(scale * shape[-1])]
+  opt.outShape = list(opt.outShape)
+  if flipped is not None:
+    flipped.blend, flipped.outShape = opt.blend, transposeShape(opt.outShape)
+    opt.transposedOpt = flipped
+  return scale, int(pad * scale)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -332,32 +336,46 @@ def doCrop(opt, x, *args, **_):
   return run_plan(opt.modelCached, x, opt.plan, out).detach()
 
 
-# dihedral test-time ensemble (imageProcess.py:558-572) — torch views around doCrop
-transpose = lambda x: x.transpose(-1, -2)
-flip = lambda x: x.flip(-1)
-flip2 = lambda x: x.flip(-1, -2)
-_combine = lambda *fs: (lambda x: _reduce(fs, x))
+# dihedral test-time ensemble (imageProcess.py:558-572): pass k of the reference applies trans[k] before doCrop and
+# transInv[k] after it; passes whose forward map swaps H and W run on the transposed plan.
+_T = lambda x: x.transpose(-1, -2)
+_FX = lambda x: x.flip(-1)
+_FXY = lambda x: x.flip(-1, -2)
+_chain = lambda *fs: (lambda x: _apply_all(fs, x))
 
 
-def _reduce(fs, x):
+def _apply_all(fs, x):
   for f in fs:
     x = f(x)
   return x
 
 
+# (forward, inverse, needs the transposed plan)
+_DIHEDRAL = [
+  (_T, _T, True),
+  (_FX, _FX, False),
+  (_FXY, _FXY, False),
+  (_chain(_FX, _T), _chain(_T, _FX), True),
+  (_chain(_T, _FX), _chain(_FX, _T), True),
+  (_chain(_T, _FX, _T), _chain(_T, _FX, _T), False),
+  (_chain(_FXY, _T), _chain(_FXY, _T), True),
+]
+trans = [d[0] for d in _DIHEDRAL]              # the reference's module-level names
+transInv = [d[1] for d in _DIHEDRAL]
 getTransposedOpt = lambda opt: opt.transposedOpt
-trans = [transpose, flip, flip2, _combine(flip, transpose), _combine(transpose, flip), _combine(transpose, flip, transpose), _combine(flip2, transpose)]
-transInv = [transpose, flip, flip2, trans[4], trans[3], trans[5], trans[6]]
-which = [getTransposedOpt, identity, identity, getTransposedOpt, getTransposedOpt, identity, getTransposedOpt]
+which = [getTransposedOpt if d[2] else identity for d in _DIHEDRAL]
+transpose, flip, flip2 = _T, _FX, _FXY
 
 
 def ensemble(opt):
-  def f(x):
-    v = doCrop(opt, x)
-    for _, t, tInv, w in zip(range(opt.ensemble), trans, transInv, which):
-      v = (v + tInv(doCrop(w(opt), t(x).contiguous()))).detach()
-    return v
-  return f
+  """x -> doCrop(x) + sum of the first opt.ensemble dihedral passes (the caller divides, runSR.sr)"""
+  def run(x):
+    total = doCrop(opt, x)
+    for forward, inverse, transposed in _DIHEDRAL[:opt.ensemble]:
+      o = opt.transposedOpt if transposed else opt
+      total = (total + inverse(doCrop(o, forward(x).contiguous()))).detach()
+    return total
+  return run
 
 
 def strengthOp(x, inp, s=1):
@@ -371,55 +389,52 @@ def strengthOp(x, inp, s=1):
   return x
 
 
-def extractAlpha(t):                           # imageProcess.py:345-352
-  def f(im):
-    if im.shape[0] == 4:
-      t['im'] = im[3]
-      return im[:3]
-    return im
-  return f
+def extractAlpha(t):
+  """imageProcess.py:345-352: park a 4th (alpha) plane in `t`, hand on the colour planes"""
+  def split(im):
+    if im.shape[0] != 4:
+      return im
+    t['im'] = im[3]
+    return im[:3]
+  return split
 
 
-def mergeAlpha(t):                             # imageProcess.py:354-363
-  def f(im):
-    if len(t):
-      image = torch.empty((4, *im.shape[1:]), dtype=im.dtype, device=im.device)
-      image[:3] = im
-      image[3] = t['im']
-      return image
-    return im
-  return f
+def mergeAlpha(t):
+  """imageProcess.py:354-363: put the parked alpha plane back behind the filtered colour planes"""
+  def join(im):
+    if not t:
+      return im
+    return torch.cat([im, t['im'].to(im.dtype).unsqueeze(0)], 0)
+  return join
 
 
-def _RGBFilter(opt, img):                      # imageProcess.py:370-377
-  t = {}
-  imgIn = opt.prepare(extractAlpha(t)(img))
-  prediction = doCrop(opt, imgIn)
-  out = strengthOp(prediction, imgIn, opt.strength)
-  return mergeAlpha(t)(out)
+def _RGBFilter(opt, img):
+  """imageProcess.py:370-377: alpha bypasses the network, colour goes through doCrop, then strengthOp"""
+  parked = {}
+  colour = opt.prepare(extractAlpha(parked)(img))
+  filtered = strengthOp(doCrop(opt, colour), colour, opt.strength)
+  return mergeAlpha(parked)(filtered)
 
 
 RGBFilter = lambda opt: lambda img: _RGBFilter(opt, img)
 
 
-class Option():                                # imageProcess.py:379-395
+class Option():
+  """imageProcess.py:379-395 — the bag of settings getOpt fills and doCrop reads.  Calling it runs the bare network
+  on one tile (`modelCached`) and returns the last element of its output list."""
+  _DEFAULTS = dict(ramCoef=1e-3, count=0, padding=1, cropsize=0, align=8, fixChannel=1, scale=1, ensemble=0, strength=1.0,
+                   outShape=None, oShape=None, iterClip=None, plan=None)
+
   def __init__(self, path=''):
-    self.ramCoef, self.count = 1e-3, 0
-    self.padding, self.cropsize, self.align, self.fixChannel = 1, 0, 8, 1
-    self.scale, self.ensemble, self.strength = 1, 0, 1.0
+    vars(self).update(self._DEFAULTS)
     self.model = path
-    self.outShape, self.oShape = None, None
-    self.iterClip = None
-    self.plan = None
     self.prepare = identity
     self.squeeze = lambda x: x.squeeze(0)
     self.unsqueeze = lambda x: x.unsqueeze(0)
 
   def __call__(self, x, *args, **kwargs):
     out = self.modelCached(x, *args, **kwargs)
-    if type(out) == list:
-      out = out[-1]
-    return out
+    return out[-1] if isinstance(out, list) else out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,49 +1,66 @@
-"""Drop-in for MoePhoto's python/runSR.py on the a*/p* models and MoeNet_lite2 (runSR.py:9-49): same module-level
-names `ramCoef`, `mode_switch`, `sr`, `getOpt`, same Option fields — backed by the sm_100a engine.
-The `gan*` rows (RRDBNet) are another model family and not on this path; getOpt returns None for
-any model+scale it does not know, exactly as the reference does for unknown names (runSR.py:35-36).
+"""Engine-backed stand-in for MoePhoto's python/runSR.py (reference: runSR.py:9-49).
+
+Public names and meanings are the reference's — `ramCoef`, `mode_switch`, `sr`, `getOpt` and the fields of the
+returned Option — because procedure.py:13-14,67,72,171 reads exactly those.  Served here: the `a*` / `p*` nets
+(models.Net2x/3x/4x) and MoeNet_lite2 (`lite2/4/8`); the `gan*` rows (RRDBNet) are another model family and stay on
+the stock code (install.py).  Like the reference (runSR.py:35-36), getOpt answers None for a model+scale it has no
+row for.
 """
 import numpy as np
-from .imageProcess import ensemble, initModel, Option
-from .models import Net2x, Net3x, Net4x, LiteNet
+
+from . import imageProcess as _ip
 from .config import config
+from .models import LiteNet, Net2x, Net3x, Net4x
 
-# bytes per input pixel-plane the reference calibrated for (CPU fp32, GPU fp32, GPU fp16), runSR.py:9.
-# Kept verbatim: it decides the tile grid, and the tile grid is part of the numerics.
-ramCoef = .9 / np.array([[10888.4, 4971.7, 2473.], [24248., 8253.9, 6120.], [41951.3, 16788.7, 7029.7],
-                         [3678., 4712.1, 3223.2], [10803., 10944., 5880.5], [40915., 50049., 27899]])   # rows 4, 6, 7 of runSR.py:9
-mode_switch = {
-  'a2': ('./model/a2/model_new.pth', Net2x, ramCoef[0]),
-  'a3': ('./model/a3/model_new.pth', Net3x, ramCoef[1]),
-  'a4': ('./model/a4/model_new.pth', Net4x, ramCoef[2]),
-  'p2': ('./model/p2/model_new.pth', Net2x, ramCoef[0]),
-  'p3': ('./model/p3/model_new.pth', Net3x, ramCoef[1]),
-  'p4': ('./model/p4/model_new.pth', Net4x, ramCoef[2]),
-  'lite2': ('./model/lite/model.pth', LiteNet, ramCoef[3]),
-  'lite4': ('./model/lite/model_4.pth', lambda: LiteNet(upscale=4), ramCoef[4]),
-  'lite8': ('./model/lite/model_8.pth', lambda: LiteNet(upscale=8), ramCoef[5]),
+# Bytes of working memory per input pixel-plane that the reference calibrated, columns = (CPU fp32, GPU fp32,
+# GPU fp16) — rows 0,1,2,4,6,7 of the table at runSR.py:9.  Kept to the digit: the numbers choose the tile grid and the
+# tile grid is part of the numerics.
+_BYTES_PER_PIXEL = {
+  'Net2x': (10888.4, 4971.7, 2473.), 'Net3x': (24248., 8253.9, 6120.), 'Net4x': (41951.3, 16788.7, 7029.7),
+  'lite2': (3678., 4712.1, 3223.2), 'lite4': (10803., 10944., 5880.5), 'lite8': (40915., 50049., 27899),
 }
+ramCoef = .9 / np.array([_BYTES_PER_PIXEL[k] for k in ('Net2x', 'Net3x', 'Net4x', 'lite2', 'lite4', 'lite8')])
 
-sr = lambda opt: (lambda x: ensemble(opt)(x) / (opt.ensemble + 1)) if opt.ensemble else ensemble(opt)
+
+def _registry():
+  rows = {}
+  for family in 'ap':                                    # runSR.py:11-16
+    for i, ctor in enumerate((Net2x, Net3x, Net4x)):
+      rows['%s%d' % (family, i + 2)] = ('./model/%s%d/model_new.pth' % (family, i + 2), ctor, ramCoef[i])
+  for i, (scale, ckpt) in enumerate(((2, 'model.pth'), (4, 'model_4.pth'), (8, 'model_8.pth'))):   # runSR.py:21-23
+    rows['lite%d' % scale] = ('./model/lite/' + ckpt, (lambda s: (lambda: LiteNet(upscale=s)))(scale), ramCoef[3 + i])
+  return rows
+
+
+mode_switch = _registry()   # name -> (checkpoint, constructor, ramCoef row), the reference's row shape
+
+
+def sr(opt):
+  """the closure procedure.py:72 composes: x (C,H,W) -> (C,s*H,s*W); with test-time ensemble the mean of the passes"""
+  run = _ip.ensemble(opt)
+  if not opt.ensemble:
+    return run
+  return lambda x: run(x) / (opt.ensemble + 1)
 
 
 def getOpt(optSR, weights=None):
-  """optSR: {'model': 'a'|'p', 'scale': 2|3|4, 'ensemble'?: 0..7}.  `weights` (a state dict) overrides
-  the checkpoint path — used by tests and benchmarks that have no MoePhoto tree around them."""
-  opt = Option()
-  opt.mode = optSR['model']
-  opt.scale = optSR['scale']
-  nmode = opt.mode + str(opt.scale)
-  if nmode not in mode_switch:
+  """optSR = {'model': 'a'|'p'|'lite', 'scale': int, 'ensemble'?: 0..7}.  `weights` (a state dict) replaces the
+  checkpoint file — tests and benchmarks run without a MoePhoto tree around them."""
+  row = mode_switch.get('{}{}'.format(optSR['model'], optSR['scale']))
+  if row is None:
     return None
-  opt.fixChannel = 0
-  opt.squeeze = lambda x: x.squeeze(1)
-  opt.unsqueeze = lambda x: x.unsqueeze(1)
-  opt.padding = 9 if opt.scale == 3 else 5
-  opt.model = mode_switch[nmode][0]
-  opt.modelDef = mode_switch[nmode][1]
-  opt.ensemble = optSR['ensemble'] if 'ensemble' in optSR and (0 <= optSR['ensemble'] <= 7) else config.ensembleSR
-  opt.ramCoef = mode_switch[nmode][2][config.getRunType()]
-  opt.cropsize = config.getConfig()[0]
-  opt.modelCached = initModel(opt, weights if weights is not None else opt.model, None if weights is not None else 'SR' + nmode)
+  checkpoint, constructor, coef = row
+  wanted = optSR.get('ensemble', None)
+  opt = _ip.Option(checkpoint)
+  vars(opt).update(
+    mode=optSR['model'], scale=optSR['scale'], modelDef=constructor,
+    fixChannel=0,                                          # planes are a batch: the budget divides by the plane count
+    squeeze=lambda x: x.squeeze(1), unsqueeze=lambda x: x.unsqueeze(1),
+    padding=9 if optSR['scale'] == 3 else 5,               # runSR.py:41
+    ensemble=wanted if wanted is not None and 0 <= wanted <= 7 else config.ensembleSR,
+    ramCoef=coef[config.getRunType()],
+    cropsize=config.getConfig()[0],
+  )
+  cache_key = None if weights is not None else 'SR{}{}'.format(optSR['model'], optSR['scale'])
+  opt.modelCached = _ip.initModel(opt, checkpoint if weights is None else weights, cache_key)
   return opt

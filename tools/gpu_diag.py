@@ -118,21 +118,26 @@ def golden_suite(eng):
 def timing(eng):
   sys.path.insert(0, os.path.join(ROOT, 'tests'))
   import helpers as Hh
-  for key, scale, shape, no_pt in (('a2', 2, (3, 1080, 1920), False), ('a4', 4, (3, 2160, 3840), True), ('a4', 4, (3, 2160, 3840), False)):
+  for key, scale, shape, no_pt in (('a2', 2, (3, 1080, 1920), False), ('lite2', 2, (3, 1080, 1920), False), ('lite4', 4, (3, 1080, 1920), False),
+                                   ('a3', 3, (3, 1080, 1920), False), ('dn_lite15', 1, (3, 1080, 1920), False), ('a4', 4, (3, 2160, 3840), False)):
     try:
       eng.set_conv_path(simt=False, no_fuse=no_pt)
-      say('[time] last upsample conv fused with the head dot products: %s' % (not no_pt))
       sd = Hh.load_weights(key)
-      opt = runSR.getOpt({'model': 'a', 'scale': scale}, weights=sd)
+      if key.startswith('dn'):
+        opt = runDN.getOpt({'model': 'lite15'}, weights=sd)
+        run = IP.RGBFilter(opt)
+      else:
+        opt = runSR.getOpt({'model': 'lite' if key.startswith('lite') else 'a', 'scale': scale}, weights=sd)
+        run = runSR.sr(opt)
       x = torch.rand(shape, device='cuda').half()
       for _ in range(2):
-        y = runSR.sr(opt)(x)
+        y = run(x)
       torch.cuda.synchronize()
       t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
       eng.profile(True)
       t0.record()
       for _ in range(3):
-        y = runSR.sr(opt)(x)
+        y = run(x)
       t1.record(); torch.cuda.synchronize()
       eng.profile(False)
       pr = eng.profile_read()
