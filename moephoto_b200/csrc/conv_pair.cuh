@@ -250,7 +250,8 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
 // The same pairing for the 64 -> 64 trunk convolutions (conv_input2 and the twelve ARSB convs): M = 256,
 // N = 64, each CTA holding HALF of the output channels' weights (32 rows of every tap).  Per MMA an SM now
 // fetches 4 KB (A) + 1 KB (B half) instead of 4 + 2 KB: 40 instead of 48.5 cycles at the operand-fetch limit.
-// Epilogue exactly as in conv_tc.cuh (plain / PReLU / x scale + residual via TMA, double-buffered staging).
+// Epilogue exactly as in conv_tc.cuh (plain / PReLU / x scale + residual via TMA / + bias, PReLU with the PixelShuffle
+// store map: the nine sub-pixel chunks of Net3x's 64 -> 576 upsample conv run as nine groups of pairs).
 struct PairTrunkCfg {
   static constexpr int kSlots = 6;
   static constexpr int kAccStages = 4;
@@ -261,8 +262,11 @@ struct PairTrunkCfg {
   static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kWBytes + kOutStages * kStageBytes + 1024;
 };
 
-// item -> (plane n, strip pair sp, rows); p.strips = number of strip pairs
+// item -> (plane n, strip pair sp, rows); p.strips = number of strip pairs.  With PixelShuffle (r > 1) the r*r
+// 64-channel chunks are the fastest-varying part of the item index and a pair keeps ONE chunk for its lifetime
+// (the host launches a multiple of r*r pairs), so `item / (r*r)` enumerates the (plane, strip pair, segment) triples.
 __device__ __forceinline__ void pair_trunk_decode(const ConvParams& p, int item, int& n, int& sp, int& y0, int& y1) {
+  item /= (p.r * p.r);
   const int seg = item % p.nseg;
   int rest = item / p.nseg;
   sp = rest % p.strips;
@@ -293,7 +297,8 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader_cta = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const CUtensorMap* omap = &maps.out[0];
+  const int chunk = pair % (p.r * p.r);            // npairs is a multiple of r*r (host)
+  const CUtensorMap* omap = &maps.out[chunk];
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
@@ -318,7 +323,7 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, Cfg::kWBytes);
       for (int tap = 0; tap < 9; ++tap)      // output channels 32*rank .. +31 of every tap
-        ptx::bulk_load_1d(wsm + tap * 4096, p.w_img + tap * 8192 + rank * 4096, 4096, wbar);
+        ptx::bulk_load_1d(wsm + tap * 4096, p.w_img + static_cast<size_t>(chunk) * kChunkImgBytes + tap * 8192 + rank * 4096, 4096, wbar);
     }
     __syncwarp();
     uint32_t ld = 0;
@@ -405,6 +410,9 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
     uint8_t* my_row = stg_ptr + L * 128;
     const int sw = L & 7;
     const uint32_t tempty_leader = ptx::mapa(tempty, 0);
+    float bias_r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias_r[j] = p.epi == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
     uint32_t acc = 0;
     // residual prefetch cursor: walks the same row sequence kSkipAhead rows ahead of the epilogue
     int c_item = pair, c_n = 0, c_sp = 0, c_y = 0, c_y1 = 0;
@@ -468,8 +476,8 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
               s0 = __low2float(hs);
               s1 = __high2float(hs);
             }
-            const float f0 = epi_apply(__uint_as_float(v[j]), p.epi, p.param, 0.f, s0);
-            const float f1 = epi_apply(__uint_as_float(v[j + 1]), p.epi, p.param, 0.f, s1);
+            const float f0 = epi_apply(__uint_as_float(v[j]), p.epi, p.param, bias_r[j], s0);
+            const float f1 = epi_apply(__uint_as_float(v[j + 1]), p.epi, p.param, bias_r[j + 1], s1);
             const __half2 hv = __floats2half2_rn(f0, f1);
             w[e] = *reinterpret_cast<const uint32_t*>(&hv);
           }

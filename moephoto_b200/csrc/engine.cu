@@ -172,13 +172,15 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
     return check_launch(e, "conv3x3_simt_kernel");
   }
   const bool pair_path = r == 2 && epi == EPI_BIAS_PRELU && !e->no_pair && e->sm_count >= 4;
-  const bool pair_trunk = r == 1 && epi != EPI_BIAS_PRELU && !e->no_pair && !e->no_pair_trunk && e->sm_count >= 4;
+  const int ncg1 = r * r;
+  const bool pair_trunk = (r == 1 ? epi != EPI_BIAS_PRELU : (r == 3 && epi == EPI_BIAS_PRELU)) && !e->no_pair && !e->no_pair_trunk &&
+                          e->sm_count / 2 >= ncg1;
   if (pair_trunk) {
-    // CTA pairs for the 64 -> 64 convolutions: 256 px x 64 channels per MMA, conv_pair.cuh
-    const int npairs = e->sm_count / 2;
+    // CTA pairs, 256 px x 64 channels per MMA (conv_pair.cuh): the 64 -> 64 convolutions, and Net3x's nine sub-pixel chunks
+    const int npairs = e->sm_count / 2 / ncg1 * ncg1;       // a multiple of r*r: a pair keeps its chunk
     const int strips1 = (W + kStripW - 1) / kStripW;
     p.strips = (strips1 + 1) / 2;                            // strip PAIRS
-    const int64_t base_items = static_cast<int64_t>(N) * p.strips;
+    const int64_t base_items = static_cast<int64_t>(N) * p.strips * ncg1;
     choose_segments(base_items, npairs, H, 8, &p.seg_rows, &p.nseg);
     const int64_t items = base_items * p.nseg;
     if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
@@ -235,7 +237,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
       MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairTrunkCfg::kSmemBytes));
       e->pair_trunk_attr_set = true;
     }
-    const int npairs = static_cast<int>(std::min<int64_t>(e->sm_count / 2, p.items));
+    const int npairs = static_cast<int>(std::min<int64_t>(e->sm_count / 2 / ncg1 * ncg1, p.items));   // p.items is a multiple of r*r
     conv3x3_pair_trunk_kernel<<<2 * npairs, kConvThreads, PairTrunkCfg::kSmemBytes, st>>>(maps, p);
     return check_launch(e, "conv3x3_pair_trunk_kernel");
   }

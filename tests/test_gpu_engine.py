@@ -407,3 +407,27 @@ def test_full_size_4k_a4_bench_workload(engine):
         assert np.abs(yc.float().cpu().numpy() - want).max() <= 1e-3
     finally:
         config.freeMemOverride = None
+
+
+def test_frame_batched_video_route_equals_per_frame_calls(engine):
+    """moephoto_b200.video.process_frames: B frames as 3B planes with the single-frame tile plan are bit-identical to the
+    reference-style per-frame loop (video.py:351-360), for a DN -> SR chain on 16-bit BGR frames, on 1 and on 2 'ranks'"""
+    from moephoto_b200 import runSR, runDN, imageProcess as IP, video
+    from moephoto_b200.config import config
+    rng = np.random.default_rng(5)
+    frames = [rng.integers(0, 65536, (40, 56, 3), dtype=np.uint16) for _ in range(5)]
+    config.freeMemOverride, config.crop_dn, config.crop_sr = int(4e9), 32, 32
+    try:
+        odn = runDN.getOpt({'model': 'lite15'}, weights=H.load_weights('dn_lite15'))
+        osr = runSR.getOpt({'model': 'a', 'scale': 2}, weights=H.load_weights('a2'))
+        want = []
+        for f in frames:                                            # the reference's loop: one frame per iteration
+            x = IP.toTorch(16, swapRB=True)(f)
+            want.append(IP.toOutput(16, swapRB=True)(runSR.sr(osr)(IP.RGBFilter(odn)(x))))
+        got = dict(video.process_frames(frames, [odn, osr], bit_depth=16, swap_rb=True, batch=3))
+        assert sorted(got) == [0, 1, 2, 3, 4] and all(np.array_equal(got[i], want[i]) for i in range(5))
+        halves = [dict(video.process_frames(frames, [odn, osr], batch=2, rank=r, world=2)) for r in range(2)]
+        assert sorted(halves[0]) == [0, 2, 4] and sorted(halves[1]) == [1, 3]
+        assert all(np.array_equal(halves[i % 2][i], want[i]) for i in range(5))
+    finally:
+        config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
