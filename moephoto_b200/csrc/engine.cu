@@ -74,6 +74,8 @@ struct MoeEngine {
   double prof_ms[4] = {0, 0, 0, 0}, prof_work[4] = {0, 0, 0, 0};
   int64_t prof_n[4] = {0, 0, 0, 0};
   // grown-on-demand device buffers of moe_enhance_host: raw in, planar in, canvas, raw out, workspace
+  cudaStream_t copy_stream = nullptr;   // moe_enhance_host: conversion + device->host copy of finished canvas columns
+  cudaEvent_t copy_event = nullptr;
   void* buf[kNumBufs] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t cap[kNumBufs] = {0, 0, 0, 0, 0};
 };
@@ -442,6 +444,8 @@ void moe_engine_destroy(MoeEngine* e)
   if (!e) return;
   Guard g(e->device);
   for (int i = 0; i < kNumBufs; ++i) if (e->buf[i]) cudaFree(e->buf[i]);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->copy_event) cudaEventDestroy(e->copy_event);
   delete e;
 }
 
@@ -582,9 +586,35 @@ size_t moe_plan_workspace_bytes(const MoeModel* m, int planes, const MoePlan* pl
   return worst + 1024;
 }
 
+}  // extern "C"
+
+namespace {
+// after_tile(ti, ctx): called on the host right after tile ti's kernels were enqueued (moe_enhance_host overlaps the
+// device->host copy of finished canvas columns with the next tile's compute)
+typedef int (*AfterTileFn)(int ti, void* ctx);
+int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t in_row_stride, int planes,
+                  void* canvas, int64_t out_plane_stride, int64_t out_row_stride,
+                  const MoePlan* plan, int row_lo, int row_hi, void* workspace, size_t workspace_bytes, void* stream,
+                  AfterTileFn after_tile, void* after_ctx);
+}  // namespace
+
+extern "C" {
+
 int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t in_row_stride, int planes,
                  void* canvas, int64_t out_plane_stride, int64_t out_row_stride,
                  const MoePlan* plan, int row_lo, int row_hi, void* workspace, size_t workspace_bytes, void* stream)
+{
+  return run_plan_core(m, in, in_plane_stride, in_row_stride, planes, canvas, out_plane_stride, out_row_stride, plan, row_lo, row_hi,
+                       workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t in_row_stride, int planes,
+                  void* canvas, int64_t out_plane_stride, int64_t out_row_stride,
+                  const MoePlan* plan, int row_lo, int row_hi, void* workspace, size_t workspace_bytes, void* stream,
+                  AfterTileFn after_tile, void* after_ctx)
 {
   int rc = validate_plan(m, plan, planes, row_lo, row_hi);
   if (rc != MOE_OK) return rc;
@@ -720,9 +750,13 @@ int moe_run_plan(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t i
       if ((rc = launch_head_tc(e, st, m, hp)) != MOE_OK) return rc;
     }
     if ((rc = check_launch(e, "head_blend_kernel")) != MOE_OK) return rc;
+    if (after_tile && (rc = after_tile(ti, after_ctx)) != MOE_OK) return rc;
   }
   return MOE_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int moe_conv3x3_c64(MoeEngine* e, const void* in, void* out, const void* skip, const void* w_img, const float* bias,
                     int n, int h, int w, int r, int epi, float param, void* stream)
@@ -782,11 +816,74 @@ static int ensure_buf(MoeEngine* e, int i, size_t bytes)
   return MOE_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// toFloat + toOutput on a column range [x0,x1) of the canvas (same arithmetic as to_output_kernel)
+template <typename T>
+__global__ void to_output_cols_kernel(const __half* src, int h, int w, int x0, int x1, float quant, T* dst)
+{
+  const int cols = x1 - x0;
+  const size_t total = static_cast<size_t>(h) * cols;
+  const size_t plane = static_cast<size_t>(h) * w;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t y = i / cols, px = y * w + x0 + (i - y * cols);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = __half2float(src[ch * plane + px]) * quant;
+      v = fminf(fmaxf(v, 0.f), quant - 1.f);
+      dst[px * 3 + ch] = static_cast<T>(v);
+    }
+  }
+}
+
+struct OverlapCtx {
+  MoeEngine* e; const MoePlan* plan; cudaStream_t compute, copy; cudaEvent_t ev;
+  const __half* canvas; uint8_t* d_out; uint8_t* host_out; int bits_out; int done_x; int row_lo, row_hi;
+};
+
+// convert + copy the canvas columns [c->done_x, x_end) once everything enqueued so far on the compute stream is done
+int flush_columns(OverlapCtx* c, int x_end)
+{
+  if (x_end <= c->done_x) return MOE_OK;
+  const MoePlan* pl = c->plan;
+  const int bpp = c->bits_out <= 8 ? 1 : 2;
+  MOE_CUDA(cudaEventRecord(c->ev, c->compute));
+  MOE_CUDA(cudaStreamWaitEvent(c->copy, c->ev, 0));
+  const int64_t threads = static_cast<int64_t>(pl->out_h) * (x_end - c->done_x);
+  const int grid = grid_for(threads, 256, c->e->sm_count);
+  const float quant = static_cast<float>(1 << c->bits_out);
+  if (bpp == 1)
+    to_output_cols_kernel<uint8_t><<<grid, 256, 0, c->copy>>>(c->canvas, pl->out_h, pl->out_w, c->done_x, x_end, quant, c->d_out);
+  else
+    to_output_cols_kernel<uint16_t><<<grid, 256, 0, c->copy>>>(c->canvas, pl->out_h, pl->out_w, c->done_x, x_end, quant, reinterpret_cast<uint16_t*>(c->d_out));
+  int rc = check_launch(c->e, "to_output_cols_kernel");
+  if (rc != MOE_OK) return rc;
+  const size_t pitch = static_cast<size_t>(pl->out_w) * 3 * bpp, off = static_cast<size_t>(c->done_x) * 3 * bpp;
+  MOE_CUDA(cudaMemcpy2DAsync(c->host_out + off, pitch, c->d_out + off, pitch, static_cast<size_t>(x_end - c->done_x) * 3 * bpp, pl->out_h,
+                             cudaMemcpyDeviceToHost, c->copy));
+  c->done_x = x_end;
+  return MOE_OK;
+}
+
+int overlap_after_tile(int ti, void* ctx)
+{
+  OverlapCtx* c = static_cast<OverlapCtx*>(ctx);
+  const MoePlan* pl = c->plan;
+  // a later tile rewrites the canvas from its own kept-region start: everything left of that is final
+  const int x_end = ti + 1 < pl->n_tiles ? tile_geom(*pl, pl->tiles[ti + 1], c->row_lo, c->row_hi).ramp_x0 : pl->out_w;
+  return flush_columns(c, x_end);
+}
+}  // namespace
+
+extern "C" {
+
 int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePlan* plan, void* host_out, int bits_out, void* stream)
 {
   int rc = validate_plan(m, plan, 3, 0, plan ? plan->out_h : 0);
   if (rc != MOE_OK) return rc;
   if (!host_in || !host_out) return fail(MOE_ERR_INVALID, "null host buffer");
+  if (bits_in < 1 || bits_in > 16 || bits_out < 1 || bits_out > 16) return fail(MOE_ERR_INVALID, "bad bit depth");
   MoeEngine* e = m->e;
   Guard guard(e->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -798,10 +895,21 @@ int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePla
     return rc;
   MOE_CUDA(cudaMemcpyAsync(e->buf[0], host_in, in_raw, cudaMemcpyHostToDevice, st));
   if ((rc = moe_to_planar_f16(e, e->buf[0], bits_in, plan->in_h, plan->in_w, 3, 0, e->buf[1], st)) != MOE_OK) return rc;
-  if ((rc = moe_run_plan(m, e->buf[1], static_cast<int64_t>(ipx), plan->in_w, 3, e->buf[2], static_cast<int64_t>(opx), plan->out_w,
-                         plan, 0, plan->out_h, e->buf[4], e->cap[4], st)) != MOE_OK) return rc;
-  if ((rc = moe_to_output(e, e->buf[2], bits_out, plan->out_h, plan->out_w, 3, 0, e->buf[3], st)) != MOE_OK) return rc;
-  MOE_CUDA(cudaMemcpyAsync(host_out, e->buf[3], out_raw, cudaMemcpyDeviceToHost, st));
+  // One row of tiles (the reference's plan for big frames: column strips): a tile's columns are final as soon as the
+  // NEXT tile's kept region starts, so their conversion and device->host copy run on a second stream under the next
+  // tile's compute.  Several tile rows: convert and copy everything at the end.
+  bool one_row = true;
+  for (int i = 0; i < plan->n_tiles; ++i) one_row = one_row && plan->tiles[i].top == 0 && plan->tiles[i].bsc == plan->out_h;
+  if (!e->copy_stream) {
+    MOE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    MOE_CUDA(cudaEventCreateWithFlags(&e->copy_event, cudaEventDisableTiming));
+  }
+  OverlapCtx ctx{e, plan, st, e->copy_stream, e->copy_event, static_cast<const __half*>(e->buf[2]), static_cast<uint8_t*>(e->buf[3]),
+                 static_cast<uint8_t*>(host_out), bits_out, 0, 0, plan->out_h};
+  if ((rc = run_plan_core(m, e->buf[1], static_cast<int64_t>(ipx), plan->in_w, 3, e->buf[2], static_cast<int64_t>(opx), plan->out_w,
+                          plan, 0, plan->out_h, e->buf[4], e->cap[4], st, one_row ? overlap_after_tile : nullptr, &ctx)) != MOE_OK) return rc;
+  if ((rc = flush_columns(&ctx, plan->out_w)) != MOE_OK) return rc;
+  MOE_CUDA(cudaStreamSynchronize(e->copy_stream));
   MOE_CUDA(cudaStreamSynchronize(st));
   return MOE_OK;
 }

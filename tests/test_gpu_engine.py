@@ -253,6 +253,27 @@ def test_host_buffer_entry_point_equals_the_api_path(engine):
     config.freeMemOverride = None
 
 
+def test_host_buffer_entry_point_overlapped_column_copies(engine):
+    """one row of column strips (the shape of the reference's plan for big frames): moe_enhance_host converts and copies
+    finished columns on a second stream while the next tile computes — same bytes as the plain path, 8- and 16-bit"""
+    from moephoto_b200 import _lib, imageProcess as IP
+    from moephoto_b200.config import config
+    opt = _sr_opt('a4', 4, crop=64, ram=int(4e9))
+    try:
+        rng = np.random.default_rng(12)
+        img = rng.integers(0, 256, (48, 300, 3), dtype=np.uint8)
+        y = IP.doCrop(opt, IP.toTorch(8)(img))
+        assert len(opt.plan.tiles) >= 4 and all(t[0] == 0 for t in opt.plan.tiles)          # a single tile row
+        for bits, dt in ((8, np.uint8), (16, np.uint16)):
+            want = IP.toOutput(bits)(y)
+            out = np.zeros((192, 1200, 3), dtype=dt)
+            _lib.check(engine.lib.moe_enhance_host(opt.modelCached.handle, img.ctypes.data_as(ctypes.c_void_p), 8, ctypes.byref(opt.plan.c),
+                                                   out.ctypes.data_as(ctypes.c_void_p), bits, None))
+            assert np.array_equal(out, want)
+    finally:
+        config.freeMemOverride = None
+
+
 def test_errors_are_status_codes_not_crashes(engine):
   from moephoto_b200 import _lib, imageProcess as IP
   opt = _sr_opt('a2', 2, ram=int(4e9))
