@@ -8,7 +8,8 @@
            the LR frame, per-rank row band + 16-px recompute halo, NCCL gather into rank 0 -> "strong".
   value  : frame resident in HBM (fp16 planar) -> stitched fp16 canvas resident in HBM on rank 0.
   e2e    : uint8 HWC frame in pinned HOST memory -> uint8 HWC result in HOST memory, through the C-ABI
-           (moe_enhance_host at N=1; toTorch -> sharded doCrop -> toOutput at N>1), copies timed.
+           (moe_enhance_host at N=1; at N>1 parallel.sharded_enhance_host: every rank converts and copies its own
+           band into a shared page-locked host frame), copies timed.
   --impl reference : the reference's CPU path (PyTorch conv2d on the host cores, fp32) restated by the
            oracle port (oracle/net.py forward_torch + oracle/tiling.py), all host threads, on a
            bounded sample of the same workload (a 256x256 crop per step).
@@ -288,22 +289,27 @@ def main():
       _lib.check(eng.lib.moe_enhance_host(opt.modelCached.handle, ctypes.c_void_p(host_in.data_ptr()), 8, ctypes.byref(plan.c),
                                           ctypes.c_void_p(host_out.data_ptr()), 8, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
       return None
-    xi = IP.toTorch(8)(host_in.numpy()) if rank == 0 else x
-    yi = PAR.sharded_doCrop(opt, xi)
-    if rank == 0:
-      q = torch.empty((H_IN * SCALE, W_IN * SCALE, 3), dtype=torch.uint8, device=dev)
-      _lib.check(eng.lib.moe_to_output(eng.handle, ctypes.c_void_p(yi.data_ptr()), 8, H_IN * SCALE, W_IN * SCALE, 3, 0,
-                                       ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-      host_out.copy_(q, non_blocking=True)
-      torch.cuda.current_stream().synchronize()
+    PAR.sharded_enhance_host(opt, host_in.numpy() if rank == 0 else None, shared_out, 8, 8)
     return None
 
   del y
+  shared_out = None
+  if world > 1:
+    # the result frame lives in a /dev/shm mapping every rank page-locks: each GPU writes its own band over its own PCIe link
+    name = 'moephoto_b200_bench_%s' % os.environ.get('MASTER_PORT', '0')
+    if rank == 0:
+      shared_out = PAR.SharedHostFrame(name, (H_IN * SCALE, W_IN * SCALE, 3), torch.uint8, create=True)
+    dist.barrier()
+    if rank != 0:
+      shared_out = PAR.SharedHostFrame(name, (H_IN * SCALE, W_IN * SCALE, 3), torch.uint8)
   for _ in range(2):
     e2e_step()
   e2e_ms, _ = timed(e2e_step, args.steps)
   e2e_val = out_mpix / (e2e_ms / args.steps / 1e3)
 
+  if shared_out is not None:
+    dist.barrier()
+    shared_out.close(unlink=(rank == 0))
   if rank != 0:
     if world > 1:
       dist.barrier()
@@ -328,7 +334,7 @@ def main():
     'clocks': clocks,
     'e2e': {'value': e2e_val, 'unit': 'MPix/s', 'ms_per_step': e2e_ms / args.steps, 'h2d_bytes_per_step': H_IN * W_IN * 3,
             'd2h_bytes_per_step': H_IN * SCALE * W_IN * SCALE * 3, 'path': 'moe_enhance_host (C ABI, pinned host uint8 in/out)' if world == 1 else
-            'toTorch -> sharded doCrop (NCCL) -> moe_to_output -> pinned host'},
+            'toTorch on rank 0 -> NCCL broadcast -> per-rank row band -> moe_to_output + D2H of each band into a shared page-locked host frame'},
     'gpu_launches': launches,
     'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_pair_trunk_kernel + conv3x3_pair_kernel + conv3x3_pair_head_kernel (all %d 3x3-convolution launches of rank 0 in the timed region)' % conv_n,
                  'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'peak_source': pk['src'],

@@ -81,3 +81,63 @@ def sharded_doCrop(opt, x, root=0, group=None, gather=True):
   opt.outShape[0] = x.size(0)
   run = lambda xi, lo, hi, canvas: IP.run_plan(opt.modelCached, xi, plan, canvas, rows=(lo, hi))
   return sharded_run(run, x, x.shape[0], plan.in_h, plan.in_w, plan.scale, root, group, None, gather).detach()
+
+
+class SharedHostFrame:
+  """A host frame every rank of the box can write: a /dev/shm mapping (MoePhoto hands frames between its processes
+  the same way, server.py:369-372 / MoePhoto.py:10-17), page-locked in every process so each GPU copies ITS band of
+  the result over ITS OWN PCIe link instead of funnelling the whole frame through rank 0."""
+
+  def __init__(self, name, shape, dtype=torch.uint8, create=False):
+    import numpy as np
+    self.path = '/dev/shm/' + name
+    nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    if create:
+      with open(self.path, 'wb') as f:
+        f.truncate(nbytes)
+    self._map = np.memmap(self.path, dtype=np.uint8, mode='r+', shape=(nbytes,))
+    self.tensor = torch.from_numpy(self._map).view(dtype).view(*shape)
+    self._registered = False
+    if torch.cuda.is_available():
+      rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+      self._registered = int(rc) == 0
+
+  def close(self, unlink=False):
+    if self._registered:
+      torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+      self._registered = False
+    if unlink:
+      import os
+      try:
+        os.unlink(self.path)
+      except OSError:
+        pass
+
+
+def sharded_enhance_host(opt, host_in, shared_out, bits_in=8, bits_out=8, root=0, group=None):
+  """host uint8/uint16 HWC frame on the root -> HWC result in `shared_out` (a SharedHostFrame every rank opened):
+  toTorch on the root, broadcast, every rank computes its row band and converts + copies it to the host itself.
+  No gather: the assembled frame only ever exists in host memory."""
+  import ctypes
+  from . import imageProcess as IP, _lib
+  rank = dist.get_rank(group)
+  dev = torch.device('cuda', torch.cuda.current_device())
+  shape = [host_in.shape[0], host_in.shape[1]] if rank == root else [0, 0]
+  if opt.plan is None or rank == root and (opt.plan.in_h, opt.plan.in_w) != tuple(shape):
+    pass                                                           # the root's frame decides; tell the others below
+  box = [shape]
+  dist.broadcast_object_list(box, src=dist.get_global_rank(group, root) if group is not None else root, group=group)
+  h, w = box[0]
+  x = IP.toTorch(bits_in)(host_in) if rank == root else torch.empty((3, h, w), dtype=torch.half, device=dev)
+  y = sharded_doCrop(opt, x, root, group, gather=False)
+  plan = opt.plan
+  lo, hi = band_rows(plan.in_h, plan.scale, dist.get_world_size(group), rank)
+  if hi > lo:
+    band = y[:, lo:hi].contiguous()
+    eng = opt.modelCached.engine
+    q = torch.empty((hi - lo, plan.out_w, 3), dtype=torch.uint8 if bits_out <= 8 else torch.int16, device=dev)
+    _lib.check(eng.lib.moe_to_output(eng.handle, ctypes.c_void_p(band.data_ptr()), int(bits_out), hi - lo, plan.out_w, 3, 0,
+                                     ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    shared_out.tensor[lo:hi].copy_(q.view(shared_out.tensor.dtype) if q.dtype != shared_out.tensor.dtype else q, non_blocking=True)
+  torch.cuda.current_stream().synchronize()
+  dist.barrier(group)                     # every band has landed in host memory
