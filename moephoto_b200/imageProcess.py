@@ -2,7 +2,7 @@
 (SURVEY.md §8a T1-T8, L3, I1-I2).  Same names, argument meaning and error behaviour:
 
   Option, initModel, prepare, prepareOpt, doCrop, ensemble, RGBFilter, strengthOp,
-  toTorch, toFloat, toOutput, getAnchors, modelCache, weightCache
+  toTorch, toFloat, toOutput, toNumPy, toBuffer, getAnchors, modelCache, weightCache
 
 What differs is where the work happens.  The reference's doCrop (imageProcess.py:157-172) is a Python
 loop launching ~50 aten kernels per tile and blending with torch ops; here the tile list is computed on
@@ -440,6 +440,24 @@ class Option():
 # ------------------------------------------------------------------------------------------------
 # frame <-> tensor conversions (imageProcess.py:238-263)
 # ------------------------------------------------------------------------------------------------
+def toNumPy(bitDepth):
+  """imageProcess.py:216-229, the video route's first step: (raw bytes, height, width) -> HWC integer frame.  The
+  reference converts to float32 on the host here; the engine keeps the integers (toTorch divides on the GPU)."""
+  dtype = np.uint8 if bitDepth <= 8 else (np.uint16 if bitDepth <= 16 else np.int32)
+  def f(args):
+    buffer, height, width = args
+    if not buffer:
+      return None
+    return np.frombuffer(buffer, dtype=dtype).reshape((height, width, 3))
+  return f
+
+
+def toBuffer(bitDepth):
+  """imageProcess.py:231-236: HWC integer frame -> raw bytes for the encoder pipe (`tostring` in the reference)"""
+  dtype = np.uint8 if bitDepth == 8 else np.uint16
+  return lambda im: None if im is None else np.ascontiguousarray(im).astype(dtype, copy=False).tobytes()
+
+
 def toTorch(bitDepth, dtype=None, device=None, swapRB=False):
   """HWC integer ndarray -> CHW fp16 tensor on the device, /255 (8 bit) or /2^bits; the integer frame
   is what crosses PCIe, the division runs on the GPU."""

@@ -87,3 +87,15 @@ def test_getOpt_unknown_models():
   assert set(runSR.mode_switch) == {'a2', 'a3', 'a4', 'p2', 'p3', 'p4', 'lite2', 'lite4', 'lite8'}
   assert runSR.mode_switch['a4'][0] == './model/a4/model_new.pth' and abs(runSR.mode_switch['a4'][2][2] - .9 / 7029.7) < 1e-12
   assert runDN.mode_switch['lite15'][3:] == (1, 7, 8)
+
+
+def test_video_route_byte_conversions():
+  """toNumPy / toBuffer (imageProcess.py:216-236): raw bgr48le bytes <-> HWC uint16 frames, bit-exact round trip"""
+  rng = np.random.default_rng(1)
+  frame = rng.integers(0, 65536, (6, 9, 3), dtype=np.uint16)
+  raw = frame.tobytes()
+  back = IP.toNumPy(16)((raw, 6, 9))
+  assert back.dtype == np.uint16 and np.array_equal(back, frame)
+  assert IP.toBuffer(16)(back) == raw and IP.toBuffer(16)(None) is None and IP.toNumPy(16)((b'', 6, 9)) is None
+  f8 = rng.integers(0, 256, (4, 5, 3), dtype=np.uint8)
+  assert IP.toBuffer(8)(IP.toNumPy(8)((f8.tobytes(), 4, 5))) == f8.tobytes()
