@@ -749,7 +749,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     } else {
       if ((rc = launch_head_tc(e, st, m, hp)) != MOE_OK) return rc;
     }
-    if ((rc = check_launch(e, "head_blend_kernel")) != MOE_OK) return rc;
+    if ((rc = check_launch(e, "head / stencil kernel")) != MOE_OK) return rc;
     if (after_tile && (rc = after_tile(ti, after_ctx)) != MOE_OK) return rc;
   }
   return MOE_OK;

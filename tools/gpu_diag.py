@@ -1,6 +1,6 @@
-"""First-contact diagnostics on a real B200 (run under gpurun).  Prints, never asserts: which tcgen05
-descriptor variant is right, how every kernel compares with the on-device SIMT cross-check and with a
-torch fp32 reference, golden parity on both conv paths, and a first timing.  Output -> gpurun_out/diag.log
+"""Diagnostics on a real B200 (run under gpurun).  Prints, never asserts: how single convolution layers compare with
+the on-device SIMT cross-check and with a torch fp32 reference, golden parity on both conv paths, and per-kernel-class
+timings of every model family.  Output -> gpurun_out/diag.log (copies of interesting runs live in profiles/).
 """
 import ctypes
 import json
