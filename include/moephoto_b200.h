@@ -25,6 +25,8 @@
  * MoeStatus and never aborts the process; moe_last_error() gives the message for the calling thread's
  * last failure.  All device pointers are on the engine's device.  `stream` is a cudaStream_t passed as
  * void* (NULL = legacy default stream); work is enqueued on it and the call does not synchronise.
+ * An engine and the models loaded into it are driven by one host thread at a time (MoePhoto's worker is a single
+ * thread, worker.py:76-94); different engines are independent.
  * There is NO CPU fallback: without a usable sm_100 device every compute entry point fails with
  * MOE_ERR_NO_DEVICE.
  */

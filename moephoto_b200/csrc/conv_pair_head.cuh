@@ -317,10 +317,13 @@ __global__ void __launch_bounds__(256) head_stencil_kernel(const HeadStencilPara
 {
   const HeadParams& g = p.g;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y, n = blockIdx.z;
+  const int n = blockIdx.z;
   if (x >= g.W) return;
-  const int cy = g.oy + y, cx = g.ox + x;
-  if (cy < g.keep_y0 || cy >= g.keep_y1 || cx < g.keep_x0 || cx >= g.keep_x1) return;
+  const int cx = g.ox + x;
+  if (cx < g.keep_x0 || cx >= g.keep_x1) return;
+  for (int y = blockIdx.y; y < g.H; y += gridDim.y) {            // gridDim.y is capped at 65535 rows
+  const int cy = g.oy + y;
+  if (cy < g.keep_y0 || cy >= g.keep_y1) continue;
   const size_t plane = static_cast<size_t>(g.H) * g.W;
   const float* bu = p.pu + static_cast<size_t>(n) * 9 * plane;
   float hsum[3];
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(256) head_stencil_kernel(const HeadStencilPara
     if (cx < g.blend_x1) v = h_round(old + h_round(g.ramp[cx - g.ramp_x0] * h_round(v - old)));
   }
   *dst = __float2half_rn(v);
+  }
 }
 
 }  // namespace moe
