@@ -268,9 +268,12 @@ def transposeShape(shape):
 
 
 def _plan_is_stale(opt, shape):
-  """the reference re-plans on first use, after 29 cached calls, or when the plane count changes — NOT when the
-  image size changes (imageProcess.py:136)"""
-  return opt.iterClip is None or opt.count > 28 or shape[0] != opt.outShape[0]
+  """the reference re-plans on first use, after 29 cached calls, or when the plane count changes (imageProcess.py:136).
+  It does NOT re-plan when the image size changes and then stitches with a stale grid; MoePhoto never hits that
+  because getOpt makes a fresh Option per request.  Here a size change re-plans instead of failing."""
+  if opt.iterClip is None or opt.count > 28 or shape[0] != opt.outShape[0]:
+    return True
+  return opt.plan is not None and (opt.plan.in_h, opt.plan.in_w) != (shape[-2], shape[-1])
 
 
 def prepareOpt(opt, shape):
@@ -284,6 +287,7 @@ def prepareOpt(opt, shape):
   except Exception:
     raise MemoryError('Can not calculate free memory.')
   opt.count = 0
+  opt.outShape = None if (opt.plan is not None and (opt.plan.in_h, opt.plan.in_w) != (shape[-2], shape[-1])) else opt.outShape
   flipped = None
   if opt.ensemble > 0:                         # the dihedral passes that transpose need a plan for the (W,H) image
     flipped = copy(opt)
