@@ -38,25 +38,74 @@ def run_step(opt, x, strength=None):
   return IP.strengthOp(y, x, s) if (plan.scale == 1 and s != 1) else y
 
 
+class _Stage:
+  """pinned host buffers + device buffers of one in-flight batch"""
+
+  def __init__(self, batch, h, w, oh, ow, bit_depth, dev):
+    dt = torch.uint8 if bit_depth <= 8 else torch.int16
+    self.host_in = torch.empty((batch, h, w, 3), dtype=dt).pin_memory()
+    self.host_out = torch.empty((batch, oh, ow, 3), dtype=dt).pin_memory()
+    self.dev_in = torch.empty((batch, h, w, 3), dtype=dt, device=dev)
+    self.dev_out = torch.empty((batch, oh, ow, 3), dtype=dt, device=dev)
+    self.done = torch.cuda.Event()
+    self.idx = []
+
+
 def process_frames(frames, opts, bit_depth=16, swap_rb=True, batch=None, rank=0, world=1):
   """frames: sequence of HWC integer arrays (bgr48le / bgr24 as video.py pipes them when swap_rb) ; opts: the Options
   of the step chain in order (e.g. [runDN.getOpt(...), runSR.getOpt(...)]).  Yields (index, HWC integer array) for
-  the frames of this rank (index % world == rank), processed `batch` frames per engine call."""
+  the frames of this rank (index % world == rank), `batch` frames per engine call.  Two batches are in flight: while
+  the GPU works on one, the host stages the next into page-locked memory and hands out the previous one's frames
+  (one H2D and one D2H copy per batch, the integer<->fp16 conversions run on the GPU)."""
   mine = [i for i in range(len(frames)) if i % world == rank]
   if not mine:
     return
   h, w = frames[mine[0]].shape[:2]
+  total_scale = 1
+  for o in opts:
+    total_scale *= o.scale
+  oh, ow = h * total_scale, w * total_scale
   if batch is None:
     free, _ = torch.cuda.mem_get_info()
-    batch = min(16, min(max_frames_per_call(o, h * s, w * s, int(free * .8)) for o, s in zip(opts, _cum_scales(opts))))
-  load, store = IP.toTorch(bit_depth, swapRB=swap_rb), IP.toOutput(bit_depth, swapRB=swap_rb)
-  for k in range(0, len(mine), batch):
-    idx = mine[k:k + batch]
-    x = torch.cat([load(frames[i]) for i in idx], 0)
+    batch = min(16, min(max_frames_per_call(o, h * s, w * s, int(free * .7)) for o, s in zip(opts, _cum_scales(opts))))
+  batch = max(1, min(batch, len(mine)))
+  eng = opts[0].modelCached.engine
+  dev = torch.device('cuda', eng.device_id)
+  npdt = np.uint8 if bit_depth <= 8 else np.uint16
+  stages = [_Stage(batch, h, w, oh, ow, bit_depth, dev) for _ in range(2)]
+  stream = lambda: ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+  def launch(st, idx):
+    st.idx = idx
+    hin = st.host_in.numpy().view(npdt)
+    for j, i in enumerate(idx):
+      hin[j] = frames[i]
+    n = len(idx)
+    st.dev_in[:n].copy_(st.host_in[:n], non_blocking=True)
+    x = torch.empty((3 * n, h, w), dtype=torch.half, device=dev)
+    for j in range(n):
+      _lib.check(eng.lib.moe_to_planar_f16(eng.handle, ctypes.c_void_p(st.dev_in[j].data_ptr()), int(bit_depth), h, w, 3, int(swap_rb),
+                                           ctypes.c_void_p(x[3 * j].data_ptr()), stream()))
     for opt in opts:
       x = run_step(opt, x)
-    for j, i in enumerate(idx):
-      yield i, store(x[3 * j:3 * j + 3])
+    for j in range(n):
+      _lib.check(eng.lib.moe_to_output(eng.handle, ctypes.c_void_p(x[3 * j].data_ptr()), int(bit_depth), oh, ow, 3, int(swap_rb),
+                                       ctypes.c_void_p(st.dev_out[j].data_ptr()), stream()))
+    st.host_out[:n].copy_(st.dev_out[:n], non_blocking=True)
+    st.done.record(torch.cuda.current_stream(dev))
+
+  def collect(st):
+    st.done.synchronize()
+    hout = st.host_out.numpy().view(npdt)
+    for j, i in enumerate(st.idx):
+      yield i, hout[j].copy()
+
+  chunks = [mine[k:k + batch] for k in range(0, len(mine), batch)]
+  launch(stages[0], chunks[0])
+  for k in range(len(chunks)):
+    if k + 1 < len(chunks):
+      launch(stages[(k + 1) % 2], chunks[k + 1])
+    yield from collect(stages[k % 2])
 
 
 def _cum_scales(opts):
