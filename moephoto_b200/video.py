@@ -51,31 +51,28 @@ class _Stage:
     self.idx = []
 
 
-def process_frames(frames, opts, bit_depth=16, swap_rb=True, batch=None, rank=0, world=1):
-  """frames: sequence of HWC integer arrays (bgr48le / bgr24 as video.py pipes them when swap_rb) ; opts: the Options
-  of the step chain in order (e.g. [runDN.getOpt(...), runSR.getOpt(...)]).  Yields (index, HWC integer array) for
-  the frames of this rank (index % world == rank), `batch` frames per engine call.  Two batches are in flight: while
-  the GPU works on one, the host stages the next into page-locked memory and hands out the previous one's frames
-  (one H2D and one D2H copy per batch, the integer<->fp16 conversions run on the GPU)."""
-  mine = [i for i in range(len(frames)) if i % world == rank]
-  if not mine:
-    return
-  h, w = frames[mine[0]].shape[:2]
-  total_scale = 1
-  for o in opts:
-    total_scale *= o.scale
-  oh, ow = h * total_scale, w * total_scale
-  if batch is None:
-    free, _ = torch.cuda.mem_get_info()
-    batch = min(16, min(max_frames_per_call(o, h * s, w * s, int(free * .7)) for o, s in zip(opts, _cum_scales(opts))))
-  batch = max(1, min(batch, len(mine)))
-  eng = opts[0].modelCached.engine
-  dev = torch.device('cuda', eng.device_id)
-  npdt = np.uint8 if bit_depth <= 8 else np.uint16
-  stages = [_Stage(batch, h, w, oh, ow, bit_depth, dev) for _ in range(2)]
-  stream = lambda: ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+class FrameBatcher:
+  """Keeps the page-locked staging buffers (allocating ~0.5 GB of pinned memory costs more than processing a batch)
+  and the device buffers alive across calls; `process(frames)` is the frame loop of video.py:349-360."""
 
-  def launch(st, idx):
+  def __init__(self, opts, height, width, bit_depth=16, swap_rb=True, batch=None):
+    self.opts, self.h, self.w, self.bit_depth, self.swap_rb = list(opts), height, width, bit_depth, swap_rb
+    scale = 1
+    for o in self.opts:
+      scale *= o.scale
+    self.oh, self.ow = height * scale, width * scale
+    if batch is None:
+      free, _ = torch.cuda.mem_get_info()
+      batch = min(16, min(max_frames_per_call(o, height * s, width * s, int(free * .7)) for o, s in zip(self.opts, _cum_scales(self.opts))))
+    self.batch = max(1, int(batch))
+    self.eng = self.opts[0].modelCached.engine
+    self.dev = torch.device('cuda', self.eng.device_id)
+    self.stages = [_Stage(self.batch, height, width, self.oh, self.ow, bit_depth, self.dev) for _ in range(2)]
+
+  def _launch(self, st, frames, idx):
+    eng, dev, h, w = self.eng, self.dev, self.h, self.w
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    npdt = np.uint8 if self.bit_depth <= 8 else np.uint16
     st.idx = idx
     hin = st.host_in.numpy().view(npdt)
     for j, i in enumerate(idx):
@@ -84,28 +81,46 @@ def process_frames(frames, opts, bit_depth=16, swap_rb=True, batch=None, rank=0,
     st.dev_in[:n].copy_(st.host_in[:n], non_blocking=True)
     x = torch.empty((3 * n, h, w), dtype=torch.half, device=dev)
     for j in range(n):
-      _lib.check(eng.lib.moe_to_planar_f16(eng.handle, ctypes.c_void_p(st.dev_in[j].data_ptr()), int(bit_depth), h, w, 3, int(swap_rb),
-                                           ctypes.c_void_p(x[3 * j].data_ptr()), stream()))
-    for opt in opts:
+      _lib.check(eng.lib.moe_to_planar_f16(eng.handle, ctypes.c_void_p(st.dev_in[j].data_ptr()), int(self.bit_depth), h, w, 3, int(self.swap_rb),
+                                           ctypes.c_void_p(x[3 * j].data_ptr()), stream))
+    for opt in self.opts:
       x = run_step(opt, x)
     for j in range(n):
-      _lib.check(eng.lib.moe_to_output(eng.handle, ctypes.c_void_p(x[3 * j].data_ptr()), int(bit_depth), oh, ow, 3, int(swap_rb),
-                                       ctypes.c_void_p(st.dev_out[j].data_ptr()), stream()))
+      _lib.check(eng.lib.moe_to_output(eng.handle, ctypes.c_void_p(x[3 * j].data_ptr()), int(self.bit_depth), self.oh, self.ow, 3, int(self.swap_rb),
+                                       ctypes.c_void_p(st.dev_out[j].data_ptr()), stream))
     st.host_out[:n].copy_(st.dev_out[:n], non_blocking=True)
     st.done.record(torch.cuda.current_stream(dev))
 
-  def collect(st):
+  def _collect(self, st, copy):
     st.done.synchronize()
-    hout = st.host_out.numpy().view(npdt)
+    hout = st.host_out.numpy().view(np.uint8 if self.bit_depth <= 8 else np.uint16)
     for j, i in enumerate(st.idx):
-      yield i, hout[j].copy()
+      yield i, (hout[j].copy() if copy else hout[j])
 
-  chunks = [mine[k:k + batch] for k in range(0, len(mine), batch)]
-  launch(stages[0], chunks[0])
-  for k in range(len(chunks)):
-    if k + 1 < len(chunks):
-      launch(stages[(k + 1) % 2], chunks[k + 1])
-    yield from collect(stages[k % 2])
+  def process(self, frames, rank=0, world=1, copy=True):
+    """yields (index, HWC integer frame) for the frames with index % world == rank.  Two batches are in flight: while
+    the GPU works on one, the host stages the next into page-locked memory and hands out the previous one's frames.
+    copy=False yields views of the staging buffer, valid until the batch after next is launched."""
+    mine = [i for i in range(len(frames)) if i % world == rank]
+    chunks = [mine[k:k + self.batch] for k in range(0, len(mine), self.batch)]
+    if not chunks:
+      return
+    self._launch(self.stages[0], frames, chunks[0])
+    for k in range(len(chunks)):
+      if k + 1 < len(chunks):
+        self._launch(self.stages[(k + 1) % 2], frames, chunks[k + 1])
+      yield from self._collect(self.stages[k % 2], copy)
+
+
+def process_frames(frames, opts, bit_depth=16, swap_rb=True, batch=None, rank=0, world=1):
+  """one-shot convenience around FrameBatcher: frames = sequence of HWC integer arrays (bgr48le / bgr24 as video.py
+  pipes them when swap_rb); opts = the Options of the step chain in order; yields (index, HWC integer frame)"""
+  if len(frames) == 0:
+    return
+  h, w = frames[0].shape[:2]
+  mine = len([i for i in range(len(frames)) if i % world == rank])
+  fb = FrameBatcher(opts, h, w, bit_depth, swap_rb, batch if batch is None else min(batch, max(1, mine)))
+  yield from fb.process(frames, rank, world)
 
 
 def _cum_scales(opts):
