@@ -35,7 +35,7 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
 METRIC = 'output MPix/s, 4x SR (a4) on 3840x2160 RGB'
 H_IN, W_IN, SCALE = 2160, 3840, 4
 FLOP_PER_LR_PIXEL_PLANE = 3945600
-CPU_SAMPLE = 256                            # the CPU legs run a CPU_SAMPLE^2 crop per step
+CPU_SAMPLE = int(os.environ.get('MOE_BENCH_CPU_SAMPLE', '256'))   # the CPU legs run a CPU_SAMPLE^2 crop per step
 
 
 def a4_weights():
