@@ -98,8 +98,12 @@ int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t 
 /* bit 0: 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (debug cross-check);
  * bit 1: 1 = keep every convolution on the single-CTA kernel instead of CTA pairs (A/B switch);
  * bit 2: 1 = only the 64->64 trunk convolutions stay on the single-CTA kernel;
- * bit 3: 1 = do not fuse the last upsample convolution with the heads' dot products */
+ * bit 3: 1 = do not fuse the last upsample convolution with the heads' dot products;
+ * bit 4: 1 = the CTA-pair kernels deal their work items round-robin instead of drawing them from a counter */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
+/* Diagnostics: `dev` = device buffer of >= 4 * 8 bytes per SM pair (or NULL to switch off).  Every CTA-pair convolution
+ * launch then leaves {start ns, end ns, SM id, items processed} per pair in it (the last launch wins). */
+int moe_engine_debug_buffer(MoeEngine* e, void* dev, size_t nbytes);
 
 /* ---- model -------------------------------------------------------------------------------- */
 /* `blob` is HOST memory in the packed format produced by moephoto_b200/weights.py (layout documented

@@ -42,6 +42,7 @@ SYMBOLS = {
   'moe_engine_profile': (_i, [_vp, _i]),
   'moe_engine_profile_read': (_i, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
   'moe_engine_set_conv_path': (_i, [_vp, _i]),
+  'moe_engine_debug_buffer': (_i, [_vp, _vp, _sz]),
   'moe_model_load': (_i, [_vp, _i, _vp, _sz, _pp]),
   'moe_model_free': (None, [_vp]),
   'moe_model_scale': (_i, [_vp]),

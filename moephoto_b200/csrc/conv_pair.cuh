@@ -24,6 +24,86 @@ struct PairCfg {
   static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kChunkImgBytes + 2 * kStageBytes + 1024;
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Item scheduler.  A launch is cut into items (a row segment of one strip pair of one plane for one chunk group);
+// a pair keeps the weights of ONE chunk group resident, so each group has its own item sequence j = 0, 1, ...
+// Dealing the items round-robin leaves SMs idle at the end of every launch — ncu showed sm__cycles_active between
+// 6.5M and 8.1M cycles across the SMs of one fused-upsample launch (profiles/r01_final_kernels_ncu.txt) although every
+// pair had the same number of rows: pairs do not run at the same speed.  So the pairs DRAW items instead: the leader
+// CTA's producer warp takes the next j of its group from a global counter (one atomicAdd per item, one item ahead of
+// its loads) and publishes the item to every warp role of both CTAs through a small shared-memory queue:
+//   items[q] (int) + bars[q] (mbarrier, count 1), q = ordinal % kSchedQ, written locally and into the peer CTA
+//   (st.shared::cluster + mbarrier.arrive.release.cluster), consumed with an acquire wait; item -1 ends the stream.
+// The queue needs no "slot free" handshake: the publisher runs at most one item ahead of the TMA producer, and the
+// slowest consumer (the P readers of the fused kernel) trails the producer by at most ring + accumulator + P stages
+// = 12 rows = 4 items of the smallest possible size (1 row + 2 halo rows), so nobody is ever kSchedQ = 16 behind.
+constexpr int kSchedQ = 16;
+constexpr int kSchedGroups = 16;                  // counters [0, 16): next j of a chunk group; [16]: finished pairs
+constexpr int kSchedInts = kSchedGroups + 1;
+
+struct PairSched {
+  uint32_t items, bars;       // shared::cta addresses of the queue in THIS CTA
+  int group, groups;          // this pair's chunk group / number of groups
+  int j_stride, j_count;      // pairs per group (= first j drawn dynamically, = static stride) / items per group
+  int* ctr;
+  int dynamic;
+};
+
+__device__ __forceinline__ PairSched sched_make(const ConvParams& p, uint32_t items, uint32_t bars, int pair, int npairs, int groups) {
+  PairSched s;
+  s.items = items; s.bars = bars;
+  s.group = pair % groups; s.groups = groups;
+  s.j_stride = npairs / groups; s.j_count = p.items / groups;
+  s.ctr = p.sched; s.dynamic = p.dynamic;
+  return s;
+}
+__device__ __forceinline__ void sched_init_bars(uint32_t bars) {      // one thread, before fence_mbar_init
+  for (int i = 0; i < kSchedQ; ++i) ptx::mbar_init(bars + 8 * i, 1);
+}
+__device__ __forceinline__ int sched_item(const PairSched& s, int j) { return j < s.j_count ? s.group + s.groups * j : -1; }
+// leader CTA's producer warp, converged: the j after `j` (the pair's first j is pair / groups)
+__device__ __forceinline__ int sched_next_j(const PairSched& s, int j, int lane) {
+  if (!s.dynamic) return j + s.j_stride;
+  int nj = 0;
+  if (lane == 0) nj = s.j_stride + atomicAdd(s.ctr + s.group, 1);
+  return __shfl_sync(0xffffffffu, nj, 0);
+}
+__device__ __forceinline__ void sched_publish(const PairSched& s, uint32_t ord, int item) {   // ONE lane of the leader's producer warp
+  const uint32_t q = ord % kSchedQ;
+  ptx::st_shared_u32(s.items + 4 * q, static_cast<uint32_t>(item));
+  ptx::st_shared_cluster_u32(ptx::mapa(s.items + 4 * q, 1), static_cast<uint32_t>(item));
+  ptx::mbar_arrive(s.bars + 8 * q);                                   // release.cta: orders the local store
+  ptx::mbar_arrive_cluster_release(ptx::mapa(s.bars + 8 * q, 1));     // release.cluster: orders the store into the peer
+}
+__device__ __forceinline__ int sched_take(const PairSched& s, uint32_t ord) {                 // any warp of either CTA, all lanes
+  const uint32_t q = ord % kSchedQ;
+  ptx::mbar_wait_cluster(s.bars + 8 * q, (ord / kSchedQ) & 1);
+  return static_cast<int>(ptx::ld_shared_u32(s.items + 4 * q));
+}
+// producer warps of both CTAs, converged: item number `ord` of this pair (ord 0 = the pair's first item, j = pair / groups)
+__device__ __forceinline__ int sched_produce(const PairSched& s, bool leader, int lane, int& j, uint32_t ord) {
+  if (!leader) return sched_take(s, ord);
+  if (ord != 0) j = sched_next_j(s, j, lane);
+  const int item = sched_item(s, j);
+  if (lane == 0) sched_publish(s, ord, item);
+  __syncwarp();
+  return item;
+}
+// end of kernel, one thread of the leader CTA: the last pair to finish zeroes the counters for the next launch
+__device__ __forceinline__ void sched_finish(const ConvParams& p, int npairs) {
+  if (!p.dynamic) return;
+  __threadfence();
+  if (atomicAdd(p.sched + kSchedGroups, 1) == npairs - 1) {
+    for (int i = 0; i < kSchedInts; ++i) p.sched[i] = 0;
+    __threadfence();
+  }
+}
+__device__ __forceinline__ void pair_debug(const ConvParams& p, int pair, uint64_t t0, int n_items) {
+  if (!p.dbg) return;
+  unsigned long long* d = p.dbg + static_cast<size_t>(pair) * 4;
+  d[0] = t0; d[1] = ptx::globaltimer_ns(); d[2] = ptx::smid(); d[3] = static_cast<unsigned long long>(n_items);
+}
+
 // item -> (chunk group g, plane n, strip pair sp, rows)
 __device__ __forceinline__ void pair_decode_item(const ConvParams& p, int item, int& g, int& n, int& sp, int& y0, int& y1) {
   g = item & 1;
@@ -52,6 +132,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
   const uint32_t wbar = tempty + 8 * AS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
   const uint32_t bias_sm = bars + 256;                              // 128 floats, 16-byte aligned for float4 reads
+  const uint32_t sq_items = bars + 768, sq_bars = bars + 832;       // item queue (kSchedQ ints + kSchedQ barriers)
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
   uint8_t* stg_ptr = smem + (stg - base);
   float* bias_ptr = reinterpret_cast<float*>(smem + (bias_sm - base));
@@ -62,6 +143,9 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int g_fixed = pair & 1;                   // npairs is even (host), so a pair keeps its chunk group
   const int my_chunk = g_fixed * 2 + static_cast<int>(rank);
+  const PairSched sc = sched_make(p, sq_items, sq_bars, pair, npairs, 2);
+  const uint64_t t_start = p.dbg ? ptx::globaltimer_ns() : 0;
+  int n_items = 0;
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
@@ -69,6 +153,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     ptx::mbar_init(wbar, 1);
     ptx::mbar_init(wpeer, 1);
     ptx::mbar_init(dbar, 1);
+    sched_init_bars(sq_bars);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&maps.in);
   }
@@ -88,11 +173,16 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
       for (int tap = 0; tap < 9; ++tap) ptx::bulk_load_1d(wsm + tap * 8192, src + tap * 8192, 8192, wbar);
     }
     __syncwarp();
-    uint32_t ld = 0;
-    for (int item = pair; item < p.items; item += npairs) {
+    uint32_t ld = 0, ord = 0;
+    int j = pair / sc.groups;
+    int item = sched_produce(sc, leader_cta, lane, j, ord++);
+    while (item >= 0) {
+      const int next_item = sched_produce(sc, leader_cta, lane, j, ord++);     // drawn one item ahead of the loads
       int g, n, sp, y0, y1;
       pair_decode_item(p, item, g, n, sp, y0, y1);
       const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      ++n_items;
+      item = next_item;
       for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
         const uint32_t slot = ld % S;
         ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
@@ -118,7 +208,8 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
       ptx::mbar_wait(wpeer, 0);
       ptx::tc_fence_after_sync();
       uint32_t cons = 0, acc = 0;
-      for (int item = pair; item < p.items; item += npairs) {
+      uint32_t ord = 0;
+      for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
         int g, n, sp, y0, y1;
         pair_decode_item(p, item, g, n, sp, y0, y1);
         const int nrows = y1 - y0;
@@ -177,7 +268,8 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     const CUtensorMap* omap0 = &maps.out[g_fixed * 2];
     const CUtensorMap* omap1 = &maps.out[g_fixed * 2 + 1];
     uint32_t acc = 0;
-    for (int item = pair; item < p.items; item += npairs) {
+    uint32_t ord = 0;
+    for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
       int g, n, sp, y0, y1;
       pair_decode_item(p, item, g, n, sp, y0, y1);
       const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
@@ -240,6 +332,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::cluster_sync_all();                          // nobody frees TMEM / exits while the peer may still use it
+  if (leader_cta && tid == 0) { sched_finish(p, npairs); pair_debug(p, pair, t_start, n_items); }
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
@@ -290,6 +383,7 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
   const uint32_t bars = stg + OS * kStageBytes;
   const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
   const uint32_t skfull = tempty + 8 * AS, wbar = skfull + 8 * OS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
+  const uint32_t sq_items = bars + 512, sq_bars = bars + 576;       // item queue (kSchedQ ints + kSchedQ barriers)
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
   uint8_t* stg_ptr = smem + (stg - base);
 
@@ -299,6 +393,9 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int chunk = pair % (p.r * p.r);            // npairs is a multiple of r*r (host)
   const CUtensorMap* omap = &maps.out[chunk];
+  const PairSched sc = sched_make(p, sq_items, sq_bars, pair, npairs, p.r * p.r);
+  const uint64_t t_start = p.dbg ? ptx::globaltimer_ns() : 0;
+  int n_items = 0;
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
@@ -307,6 +404,7 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
     ptx::mbar_init(wbar, 1);
     ptx::mbar_init(wpeer, 1);
     ptx::mbar_init(dbar, 1);
+    sched_init_bars(sq_bars);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&maps.in);
     ptx::prefetch_tmap(omap);
@@ -326,11 +424,16 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
         ptx::bulk_load_1d(wsm + tap * 4096, p.w_img + static_cast<size_t>(chunk) * kChunkImgBytes + tap * 8192 + rank * 4096, 4096, wbar);
     }
     __syncwarp();
-    uint32_t ld = 0;
-    for (int item = pair; item < p.items; item += npairs) {
+    uint32_t ld = 0, ord = 0;
+    int j = pair / sc.groups;
+    int item = sched_produce(sc, leader_cta, lane, j, ord++);
+    while (item >= 0) {
+      const int next_item = sched_produce(sc, leader_cta, lane, j, ord++);     // drawn one item ahead of the loads
       int n, sp, y0, y1;
       pair_trunk_decode(p, item, n, sp, y0, y1);
       const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      ++n_items;
+      item = next_item;
       for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
         const uint32_t slot = ld % S;
         ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
@@ -354,7 +457,8 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
       ptx::mbar_wait(wpeer, 0);
       ptx::tc_fence_after_sync();
       uint32_t cons = 0, acc = 0;
-      for (int item = pair; item < p.items; item += npairs) {
+      uint32_t ord = 0;
+      for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
         int n, sp, y0, y1;
         pair_trunk_decode(p, item, n, sp, y0, y1);
         const int nrows = y1 - y0;
@@ -415,9 +519,10 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
     for (int j = 0; j < 32; ++j) bias_r[j] = p.epi == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
     uint32_t acc = 0;
     // residual prefetch cursor: walks the same row sequence kSkipAhead rows ahead of the epilogue
-    int c_item = pair, c_n = 0, c_sp = 0, c_y = 0, c_y1 = 0;
-    uint32_t c_idx = 0;
-    bool c_ok = has_skip && lead_warp && c_item < p.items;
+    int c_item = -1, c_n = 0, c_sp = 0, c_y = 0, c_y1 = 0;
+    uint32_t c_idx = 0, c_ord = 0;
+    bool c_ok = has_skip && lead_warp;
+    if (c_ok) { c_item = sched_take(sc, c_ord++); c_ok = c_item >= 0; }
     if (c_ok) pair_trunk_decode(p, c_item, c_n, c_sp, c_y, c_y1);
     auto prefetch_skip = [&]() {            // lead warp, converged: issue the residual load of row c_idx and advance
       if (!c_ok) return;
@@ -428,14 +533,15 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
       }
       __syncwarp();
       ++c_idx;
-      if (++c_y >= c_y1) {
-        c_item += npairs;
-        c_ok = c_item < p.items;
+      if (++c_y >= c_y1) {                   // the item after this one was published before this one's loads began
+        c_item = sched_take(sc, c_ord++);
+        c_ok = c_item >= 0;
         if (c_ok) pair_trunk_decode(p, c_item, c_n, c_sp, c_y, c_y1);
       }
     };
     if (lead_warp) for (int i = 0; i < Cfg::kSkipAhead; ++i) prefetch_skip();
-    for (int item = pair; item < p.items; item += npairs) {
+    uint32_t ord = 0;
+    for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
       int n, sp, y0, y1;
       pair_trunk_decode(p, item, n, sp, y0, y1);
       const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
@@ -507,6 +613,7 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::cluster_sync_all();
+  if (leader_cta && tid == 0) { sched_finish(p, npairs); pair_debug(p, pair, t_start, n_items); }
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);

@@ -54,6 +54,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
   const uint32_t staged = tempty + 8 * AS, pfull = staged + 8 * PS, pempty = pfull + 8 * PS;
   const uint32_t wbar = pempty + 8 * PS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
+  const uint32_t sq_items = bars + 256, sq_bars = bars + 320;       // item queue (kSchedQ ints + kSchedQ barriers), ends at +448
   const uint32_t bias_sm = bars + 512;                              // 128 floats, 16-byte aligned
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
   uint8_t* stg_ptr = smem + (stg - base);
@@ -65,6 +66,9 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int g_fixed = pair & 1;                   // npairs is even (host): a pair keeps its chunk group
   const int my_chunk = g_fixed * 2 + static_cast<int>(rank);
+  const PairSched sc = sched_make(p, sq_items, sq_bars, pair, npairs, 2);
+  const uint64_t t_start = p.dbg ? ptx::globaltimer_ns() : 0;
+  int n_items = 0;
 
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { ptx::mbar_init(full + 8 * i, 1); ptx::mbar_init(empty + 8 * i, 1); }
@@ -73,6 +77,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
     ptx::mbar_init(wbar, 1);
     ptx::mbar_init(wpeer, 1);
     ptx::mbar_init(dbar, 1);
+    sched_init_bars(sq_bars);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&maps.in);
   }
@@ -93,11 +98,16 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
       ptx::bulk_load_1d(hsm, hp.head_img + rank * 1024, 1024, wbar);       // taps 8*rank .. 8*rank+7
     }
     __syncwarp();
-    uint32_t ld = 0;
-    for (int item = pair; item < p.items; item += npairs) {
+    uint32_t ld = 0, ord = 0;
+    int j = pair / sc.groups;
+    int item = sched_produce(sc, leader_cta, lane, j, ord++);
+    while (item >= 0) {
+      const int next_item = sched_produce(sc, leader_cta, lane, j, ord++);     // drawn one item ahead of the loads
       int g, n, sp, y0, y1;
       pair_decode_item(p, item, g, n, sp, y0, y1);
       const int x0 = (sp * 2 + static_cast<int>(rank)) * kStripW;
+      ++n_items;
+      item = next_item;
       for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
         const uint32_t slot = ld % S;
         ptx::mbar_wait(empty + 8 * slot, ((ld / S) & 1) ^ 1);
@@ -122,7 +132,8 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
       ptx::mbar_wait(wpeer, 0);
       ptx::tc_fence_after_sync();
       uint32_t cons = 0, acc = 0;
-      for (int item = pair; item < p.items; item += npairs) {
+      uint32_t ord = 0;
+      for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
         int g, n, sp, y0, y1;
         pair_decode_item(p, item, g, n, sp, y0, y1);
         const int nrows = y1 - y0;
@@ -177,7 +188,8 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
     const uint32_t staged_leader = ptx::mapa(staged, 0);
     const float* my_bias = bias_ptr + ch * 64;
     uint32_t acc = 0;
-    for (int item = pair; item < p.items; item += npairs) {
+    uint32_t ord = 0;
+    for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
       int g, n, sp, y0, y1;
       pair_decode_item(p, item, g, n, sp, y0, y1);
       for (int y = y0; y < y1; ++y, ++acc) {
@@ -231,7 +243,8 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
       ptx::mbar_wait(wbar, 0);
       ptx::mbar_wait(wpeer, 0);
       uint32_t acc = 0;
-      for (int item = pair; item < p.items; item += npairs) {
+      uint32_t ord = 0;
+      for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
         int g, n, sp, y0, y1;
         pair_decode_item(p, item, g, n, sp, y0, y1);
         for (int y = y0; y < y1; ++y, ++acc) {
@@ -262,7 +275,8 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
     const int Ho = p.H * 2, Wo = p.W * 2;
     const size_t plane = static_cast<size_t>(Ho) * Wo;
     uint32_t acc = 0;
-    for (int item = pair; item < p.items; item += npairs) {
+    uint32_t ord = 0;
+    for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
       int g, n, sp, y0, y1;
       pair_decode_item(p, item, g, n, sp, y0, y1);
       const int x = (sp * 2 + static_cast<int>(rank)) * kStripW + L;
@@ -300,6 +314,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::cluster_sync_all();
+  if (leader_cta && tid == 0) { sched_finish(p, npairs); pair_debug(p, pair, t_start, n_items); }
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);

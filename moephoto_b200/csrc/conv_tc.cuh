@@ -42,6 +42,10 @@ struct ConvParams {
   float param;            // PReLU slope or residual scale
   int strips, nseg, seg_rows, items;
   int center_only;        // 1: a 1x1 convolution packed as a centre-tap 3x3 filter (MoeNet_lite2): issue only tap (1,1)
+  // pair kernels only (conv_pair.cuh, "item scheduler"):
+  int dynamic;            // 1: pairs draw their next item from the global counters, 0: round-robin by pair index
+  int* sched;             // device int[kSchedInts]: per-chunk-group item counters + the count of finished pairs; all 0 between launches
+  unsigned long long* dbg;// optional [pairs][4]: start ns, end ns, SM id, items processed (moe_engine_debug_buffer)
 };
 
 struct ConvMaps {

@@ -65,6 +65,9 @@ struct MoeEngine {
   int no_pair = 0;         // 1 = keep every conv on the single-CTA kernel (A/B switch)
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
   int no_fuse = 0;         // 1 = last upsample conv and heads stay separate kernels (conv3x3_pair_kernel + head_tc_kernel)
+  int static_sched = 0;    // 1 = pair kernels deal their items round-robin instead of drawing them (conv_pair.cuh, item scheduler)
+  int* d_sched = nullptr;  // the item scheduler's counters (kSchedInts ints, zero between launches)
+  unsigned long long* dbg = nullptr;   // moe_engine_debug_buffer: per-pair {start ns, end ns, SM id, items} of the LAST pair-kernel launch
   bool pair_head_attr_set = false;
   bool pair_trunk_attr_set = false;
   // optional per-launch CUDA-event timing (moe_engine_profile): class 0 conv_input, 1 conv3x3 r=1, 2 heads, 3 upsample conv3x3
@@ -166,6 +169,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   ConvParams p{};
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
   p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param; p.center_only = center_only;
+  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg;
   // algorithmic FLOPs: 2 * taps * Cin * Cout per input pixel (padded channels are not counted)
   Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
   if (e->simt) {
@@ -268,6 +272,7 @@ int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
   p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
+  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg;
   hp.head_img = head_img; hp.pbuf = pbuf; hp.accumulate = accumulate;
   Timed timed(e, st, 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
   const int npairs_max = (e->sm_count / 2) & ~1;
@@ -433,6 +438,12 @@ int moe_engine_create(int device_id, MoeEngine** out)
     return fail(MOE_ERR_CUDA, "driver has no cuTensorMapEncodeTiled");
   }
   e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (cudaMalloc(&e->d_sched, kSchedInts * sizeof(int)) != cudaSuccess || cudaMemset(e->d_sched, 0, kSchedInts * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    if (e->d_sched) cudaFree(e->d_sched);
+    delete e;
+    return fail(MOE_ERR_NOMEM, "scheduler counter allocation failed");
+  }
   const char* env = getenv("MOE_B200_SIMT");
   e->simt = env && env[0] == '1';
   *out = e;
@@ -444,6 +455,7 @@ void moe_engine_destroy(MoeEngine* e)
   if (!e) return;
   Guard g(e->device);
   for (int i = 0; i < kNumBufs; ++i) if (e->buf[i]) cudaFree(e->buf[i]);
+  if (e->d_sched) cudaFree(e->d_sched);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->copy_event) cudaEventDestroy(e->copy_event);
   delete e;
@@ -484,6 +496,16 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   e->no_pair = (simt >> 1) & 1;
   e->no_pair_trunk = (simt >> 2) & 1;
   e->no_fuse = (simt >> 3) & 1;
+  e->static_sched = (simt >> 4) & 1;
+  return MOE_OK;
+}
+
+int moe_engine_debug_buffer(MoeEngine* e, void* dev, size_t nbytes)
+{
+  if (!e) return fail(MOE_ERR_INVALID, "engine is null");
+  if (dev && nbytes < static_cast<size_t>(e->sm_count / 2) * 4 * sizeof(unsigned long long))
+    return fail(MOE_ERR_INVALID, "debug buffer needs %zu bytes", static_cast<size_t>(e->sm_count / 2) * 4 * sizeof(unsigned long long));
+  e->dbg = static_cast<unsigned long long*>(dev);
   return MOE_OK;
 }
 

@@ -62,9 +62,16 @@ class Engine:
     d['conv3x3'] = tuple(a + b for a, b in zip(d['conv_trunk'], d['conv_up']))      # every 3x3 tensor-core convolution
     return d
 
-  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False):
+  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False, static_sched=False):
     _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(no_pair)) << 1) | (int(bool(no_pair_trunk)) << 2) |
-                                                 (int(bool(no_fuse)) << 3)))
+                                                 (int(bool(no_fuse)) << 3) | (int(bool(static_sched)) << 4)))
+
+  def debug_buffer(self, tensor):
+    """tensor: int64 CUDA tensor of >= 4 values per SM pair, or None; see moe_engine_debug_buffer"""
+    if tensor is None:
+      _lib.check(self.lib.moe_engine_debug_buffer(self.handle, None, 0))
+    else:
+      _lib.check(self.lib.moe_engine_debug_buffer(self.handle, ctypes.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size()))
 
   def get_workspace(self, nbytes):
     if self.workspace is None or self.workspace.numel() < nbytes:
