@@ -321,51 +321,100 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   }
 }
 
-// out(Y,X) = round16( sum_{dy,dx} P[dy*3+dx](Y+dy-1, X+dx-1) ), P = P_u + P_r,, zero outside the computed rectangle,
-// then the seam blend and the canvas store of head_blend_kernel / head_tc_kernel.  One thread per output pixel.
+// out(Y,X) = round16( sum_{dy,dx} P[dy*3+dx](Y+dy-1, X+dx-1) ), P = P_u + P_r, zero outside the computed rectangle,
+// then the seam blend and the canvas store of head_blend_kernel / head_tc_kernel.
+// A thread owns 4 consecutive pixels of a row: per tap plane ONE aligned 16-byte load (two 8-byte loads when the row
+// pitch is not a multiple of 4 floats); the dx = -1 / +1 taps take their fourth value from the neighbouring lane
+// (shuffle; the warp's edge lanes load it).  A block therefore reads 2 KB of contiguous floats per plane row instead of
+// the 1 KB of misaligned 4-byte loads of the one-pixel-per-thread version (3.6 TB/s, profiles/r01_bench_n1_final.json).
 struct HeadStencilParams {
   HeadParams g;            // geometry, seam and canvas (u/r/wu/wr unused)
   const float* pu;         // [N][9][H][W]: P_u + P_r (the second branch's kernel accumulated onto the first's)
 };
 
-__global__ void __launch_bounds__(256) head_stencil_kernel(const HeadStencilParams p)
+constexpr int kStencilThreads = 128;
+constexpr int kStencilPx = 4;
+
+__global__ void __launch_bounds__(kStencilThreads) head_stencil_kernel(const HeadStencilParams p)
 {
   const HeadParams& g = p.g;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int x = (blockIdx.x * kStencilThreads + threadIdx.x) * kStencilPx;
   const int n = blockIdx.z;
-  if (x >= g.W) return;
-  const int cx = g.ox + x;
-  if (cx < g.keep_x0 || cx >= g.keep_x1) return;
-  for (int y = blockIdx.y; y < g.H; y += gridDim.y) {            // gridDim.y is capped at 65535 rows
-  const int cy = g.oy + y;
-  if (cy < g.keep_y0 || cy >= g.keep_y1) continue;
   const size_t plane = static_cast<size_t>(g.H) * g.W;
   const float* bu = p.pu + static_cast<size_t>(n) * 9 * plane;
-  float hsum[3];
+  const bool vec4 = (g.W & 3) == 0 && (reinterpret_cast<uintptr_t>(bu) & 15) == 0 && (plane & 3) == 0;   // rows of every plane 16-byte aligned
+  const int nvalid = min(kStencilPx, g.W - x);       // <= 0: this thread is right of the rectangle (it still shuffles)
+  // the whole warp must reach the shuffles: no early return
+  for (int y = blockIdx.y; y < g.H; y += gridDim.y) {            // gridDim.y is capped at 65535 rows
+    const int cy = g.oy + y;
+    const bool row_kept = cy >= g.keep_y0 && cy < g.keep_y1;     // uniform over the block
+    if (!row_kept) continue;
+    float acc[3][kStencilPx];                                    // [dy][pixel]: (t(dx=0) + t(dx=1)) + t(dx=2), as head_blend_kernel
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int yy = y + dy - 1;
-    float t3[3] = {0.f, 0.f, 0.f};
-    if (yy >= 0 && yy < g.H) {
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      const bool in_y = yy >= 0 && yy < g.H;                     // uniform over the block
+      float s[3][kStencilPx];
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const int xx = x + dx - 1;
-        if (xx >= 0 && xx < g.W) {
-          const size_t o = static_cast<size_t>(dy * 3 + dx) * plane + static_cast<size_t>(yy) * g.W + xx;
-          t3[dx] = __ldg(bu + o);
+        float v[kStencilPx] = {0.f, 0.f, 0.f, 0.f};
+        const float* row = bu + static_cast<size_t>(dy * 3 + dx) * plane + static_cast<size_t>(in_y ? yy : 0) * g.W;
+        if (in_y && nvalid > 0) {
+          if (nvalid == kStencilPx && vec4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(row + x));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          } else if (nvalid == kStencilPx && ((reinterpret_cast<uintptr_t>(row + x) & 7) == 0)) {
+            const float2 q0 = __ldg(reinterpret_cast<const float2*>(row + x));
+            const float2 q1 = __ldg(reinterpret_cast<const float2*>(row + x + 2));
+            v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+          } else {
+#pragma unroll
+            for (int i = 0; i < kStencilPx; ++i) if (i < nvalid) v[i] = __ldg(row + x + i);
+          }
+        }
+        if (dx == 1) {
+#pragma unroll
+          for (int i = 0; i < kStencilPx; ++i) s[1][i] = v[i];
+        } else if (dx == 0) {                                    // pixel i needs column x + i - 1
+          float left = __shfl_up_sync(0xffffffffu, v[3], 1);
+          if (lane == 0) left = (in_y && nvalid > 0 && x > 0) ? __ldg(row + x - 1) : 0.f;
+          s[0][0] = left; s[0][1] = v[0]; s[0][2] = v[1]; s[0][3] = v[2];
+        } else {                                                 // pixel i needs column x + i + 1
+          float right = __shfl_down_sync(0xffffffffu, v[0], 1);
+          if (lane == 31) right = (in_y && x + kStencilPx < g.W) ? __ldg(row + x + kStencilPx) : 0.f;
+          s[2][0] = v[1]; s[2][1] = v[2]; s[2][2] = v[3]; s[2][3] = right;
         }
       }
+#pragma unroll
+      for (int i = 0; i < kStencilPx; ++i) acc[dy][i] = (s[0][i] + s[1][i]) + s[2][i];
     }
-    hsum[dy] = (t3[0] + t3[1]) + t3[2];
-  }
-  float v = h_round((hsum[0] + hsum[1]) + hsum[2]);
-  __half* dst = g.canvas + n * g.plane_stride + static_cast<int64_t>(cy) * g.row_stride + cx;
-  if (cy < g.blend_y1 || cx < g.blend_x1) {
-    const float old = __half2float(*dst);
-    if (cy < g.blend_y1) v = h_round(old + h_round(g.ramp[cy - g.ramp_y0] * h_round(v - old)));
-    if (cx < g.blend_x1) v = h_round(old + h_round(g.ramp[cx - g.ramp_x0] * h_round(v - old)));
-  }
-  *dst = __float2half_rn(v);
+    if (nvalid <= 0) continue;
+    __half* dst = g.canvas + n * g.plane_stride + static_cast<int64_t>(cy) * g.row_stride + (g.ox + x);
+    float out[kStencilPx];
+    bool keep[kStencilPx];
+#pragma unroll
+    for (int i = 0; i < kStencilPx; ++i) {
+      const int cx = g.ox + x + i;
+      keep[i] = i < nvalid && cx >= g.keep_x0 && cx < g.keep_x1;
+      float v = h_round((acc[0][i] + acc[1][i]) + acc[2][i]);
+      if (keep[i] && (cy < g.blend_y1 || cx < g.blend_x1)) {
+        const float old = __half2float(dst[i]);
+        if (cy < g.blend_y1) v = h_round(old + h_round(g.ramp[cy - g.ramp_y0] * h_round(v - old)));
+        if (cx < g.blend_x1) v = h_round(old + h_round(g.ramp[cx - g.ramp_x0] * h_round(v - old)));
+      }
+      out[i] = v;
+    }
+    if (keep[0] && keep[1] && keep[2] && keep[3] && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+      const __half2 h0 = __floats2half2_rn(out[0], out[1]), h1 = __floats2half2_rn(out[2], out[3]);
+      uint2 w;
+      w.x = *reinterpret_cast<const uint32_t*>(&h0);
+      w.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(dst) = w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kStencilPx; ++i) if (keep[i]) dst[i] = __float2half_rn(out[i]);
+    }
   }
 }
 

@@ -759,10 +759,10 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     if (fuse) {
       HeadStencilParams sp{};
       sp.g = hp; sp.pu = pbuf;
-      dim3 sgrid((hp.W + 255) / 256, std::min(hp.H, 65535), N);
+      dim3 sgrid((hp.W + kStencilThreads * kStencilPx - 1) / (kStencilThreads * kStencilPx), std::min(hp.H, 65535), N);
       if (sgrid.z > 65535u) return fail(MOE_ERR_INVALID, "too many planes for the stencil kernel grid");
       Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (36 + 2));   // bytes: one 9-float read, one fp16 write
-      head_stencil_kernel<<<sgrid, 256, 0, st>>>(sp);
+      head_stencil_kernel<<<sgrid, kStencilThreads, 0, st>>>(sp);
     } else if (e->simt) {
       dim3 hgrid((hp.W + 127) / 128, hp.H, N);
       if (hgrid.y > 65535u || hgrid.z > 65535u) return fail(MOE_ERR_INVALID, "tile too tall for the head kernel grid");
