@@ -26,7 +26,8 @@
  * last failure.  All device pointers are on the engine's device.  `stream` is a cudaStream_t passed as
  * void* (NULL = legacy default stream); work is enqueued on it and the call does not synchronise.
  * An engine and the models loaded into it are driven by one host thread at a time (MoePhoto's worker is a single
- * thread, worker.py:76-94); different engines are independent.
+ * thread, worker.py:76-94) and by ONE stream at a time: its convolution launches share the work-item counters of the
+ * engine and its workspace, so two of them must not run concurrently; different engines are independent.
  * There is NO CPU fallback: without a usable sm_100 device every compute entry point fails with
  * MOE_ERR_NO_DEVICE.
  */
