@@ -332,7 +332,7 @@ def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
     config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
 
 
-@pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True)])
+@pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True), dict(static_sched=True)])
 @pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'lite2_tiled', 'lite8_single'])
 def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags):
     """the A/B switches keep the single-CTA conv kernel, the unfused CTA-pair kernel and head_tc_kernel alive;
@@ -348,6 +348,8 @@ def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags
     assert np.abs(y - orc).max() <= 1e-3
     assert H.psnr(y, c['ref']) >= 60.0
     assert np.abs(y - y_default).max() <= 1e-3
+    if flags.get('static_sched'):
+        assert np.array_equal(y, y_default)          # who computes an item never changes its result
 
 
 def test_fused_path_at_4k_tile_width(engine):
