@@ -135,6 +135,144 @@ __global__ void __launch_bounds__(64, 1) rate_kernel(long long* cycles, int iter
   if (threadIdx.x < 32) ptx::tmem_dealloc(tmem, 512);
 }
 
+// MODE 3 of the rate test: four loader warps copy every input row into TMEM themselves (ld.shared of the swizzled row,
+// three dx views, tcgen05.st) one row ahead of the MMA warp; afull / aempty mbarriers hand the 4 TMEM row buffers over.
+// Also verifies the result of the last row against the .ss MMA (bad[0] = mismatches).
+__global__ void __launch_bounds__(160, 1) st_rate_kernel(long long* cycles, int iters, int* bad)
+{
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_sm = base, b_sm = base + 3 * 17408, bars = b_sm + 9 * 8192;
+  const uint32_t afull = bars, aempty = bars + 32, done = bars + 64, tslot = bars + 72;
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
+  for (int i = threadIdx.x; i < 3 * 130 * 64; i += blockDim.x) {
+    const int r = i / (130 * 64), pc = i % (130 * 64);
+    put_sw128(smem + r * 17408, pc >> 6, pc & 63, a_val((pc >> 6) + r, pc & 63));
+  }
+  for (int i = threadIdx.x; i < 9 * 64 * 64; i += blockDim.x) {
+    const int t = i / 4096, nc = i % 4096;
+    put_sw128(smem + 3 * 17408 + t * 8192, nc >> 6, nc & 63, b_val((nc >> 6) + t, nc & 63));
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(afull + 8 * i, 4); ptx::mbar_init(aempty + 8 * i, 1); }
+    ptx::mbar_init(done, 1);
+    ptx::fence_mbar_init();
+  }
+  ptx::fence_proxy_async_smem();
+  if (threadIdx.x < 32) ptx::tmem_alloc(tslot, 512);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = *tslot_ptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t idesc = ptx::idesc_f16_f32(128, 64);
+  const uint64_t a0 = ptx::smem_desc_sw128(a_sm, 1024, 0), b0 = ptx::smem_desc_sw128(b_sm, 1024, 0);
+  if (warp == 0) {
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      // rows it-2, it-1, it must be in TMEM (rows < 0 are never loaded: skip their taps)
+      ptx::mbar_wait(afull + 8 * (it & 3), (it >> 2) & 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d = tmem + 384 + (it & 1) * 64;
+      if (ptx::elect_one()) {
+        bool first = true;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const int row = it - 2 + dy;
+          if (row < 0) continue;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ptx::mma_f16_ts(d, tmem + (row & 3) * 96 + dx * 32 + k * 8, b0 + (dy * 3 + dx) * 512 + k * 2, idesc, first ? 0u : 1u);
+              first = false;
+            }
+        }
+        // buffer of row it-2 is free once these MMAs completed
+        if (it >= 2) ptx::mma_commit(aempty + 8 * ((it - 2) & 3));
+      }
+      __syncwarp();
+    }
+    if (ptx::elect_one()) ptx::mma_commit(done);
+    __syncwarp();
+    ptx::mbar_wait(done, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  } else {
+    const int quad = warp & 3, L = quad * 32 + lane;          // TMEM lane = pixel
+    for (int it = 0; it < iters; ++it) {
+      const int b = it & 3;
+      if (it >= 4) ptx::mbar_wait(aempty + 8 * b, ((it - 4) >> 2) & 1);    // row it-4 (same buffer) has been consumed
+      ptx::tc_fence_after_sync();
+      const uint8_t* slot = smem + (it % 3) * 17408;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int p = L + dx;
+        uint32_t v[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint4 q = *reinterpret_cast<const uint4*>(slot + p * 128 + ((g ^ (p & 7)) << 4));
+          v[g * 4] = q.x; v[g * 4 + 1] = q.y; v[g * 4 + 2] = q.z; v[g * 4 + 3] = q.w;
+        }
+        ptx::tmem_st32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + b * 96 + dx * 32, v);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(afull + 8 * b);
+    }
+  }
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  // check the last accumulator against the scalar reference (rows it-2..it of the last iteration)
+  if (warp >= 1 && bad) {
+    const int quad = warp & 3, p = quad * 32 + lane, it = iters - 1;
+    for (int h = 0; h < 2; ++h) {
+      uint32_t vs[32];
+      ptx::tmem_ld32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + 384 + (it & 1) * 64 + h * 32, vs);
+      ptx::tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) {
+        const int n = h * 32 + j;
+        float want = 0.f;
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx)
+            for (int c = 0; c < 64; ++c) want += a_val(p + dx + (it - 2 + dy) % 3, c) * b_val(n + dy * 3 + dx, c);
+        if (__uint_as_float(vs[j]) != want) atomicAdd(bad, 1);
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc(tmem, 512);
+}
+
+void run_st(int grid)
+{
+  long long* d; cudaMalloc(&d, grid * sizeof(long long));
+  int* bad; cudaMalloc(&bad, sizeof(int)); cudaMemset(bad, 0, sizeof(int));
+  const int smem = 1024 + 3 * 17408 + 9 * 8192 + 128;
+  cudaFuncSetAttribute(st_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int iters = 2000;
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    st_rate_kernel<<<grid, 160, smem>>>(d, iters, bad);
+    cudaEventRecord(b);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    long long h[256]; cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+    int hb = 0; cudaMemcpy(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost);
+    double cyc = 0; for (int i = 0; i < grid; ++i) cyc += h[i]; cyc /= grid;
+    const double mmas = 36.0 * iters;
+    printf("%-44s grid=%3d rep=%d  %s  %.1f cyc/MMA (math 32)  %.3f ms  %.0f TFLOP/s  mismatches %d of %d\n", "N=64 .ts, rows copied by 4 warps (tcgen05.st)", grid, rep,
+           cudaGetErrorString(e), cyc / mmas, ms, 2.0 * 128 * 64 * 16 * mmas * grid / ms / 1e9, hb, 8192 * grid * (rep + 1));
+    if (e != cudaSuccess) break;
+  }
+  cudaFree(d); cudaFree(bad);
+}
+
 template <int MODE> void run(int grid, const char* name)
 {
   long long* d; cudaMalloc(&d, grid * sizeof(long long));
@@ -173,5 +311,7 @@ int main()
   run<1>(148, "N=64 .ts (A resident in TMEM)");
   run<2>(148, "N=64 .ts + 12 tcgen05.cp.128x256b per row");
   run<2>(1, "N=64 .ts + copies, single CTA");
+  run_st(148);
+  run_st(1);
   return 0;
 }
