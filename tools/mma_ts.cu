@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(64, 1) rate_kernel(long long* cycles, int iter
 // MODE 3 of the rate test: four loader warps copy every input row into TMEM themselves (ld.shared of the swizzled row,
 // three dx views, tcgen05.st) one row ahead of the MMA warp; afull / aempty mbarriers hand the 4 TMEM row buffers over.
 // Also verifies the result of the last row against the .ss MMA (bad[0] = mismatches).
-__global__ void __launch_bounds__(160, 1) st_rate_kernel(long long* cycles, int iters, int* bad)
+template <int GROUPS, int WHAT = 3>   // GROUPS 1: four loader warps copy all three views; 3: twelve loader warps, one view each.  WHAT bit 0: ld.shared, bit 1: tcgen05.st
+__global__ void __launch_bounds__(32 + 128 * GROUPS, 1) st_rate_kernel(long long* cycles, int iters, int* bad)
 {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(160, 1) st_rate_kernel(long long* cycles, int 
     put_sw128(smem + 3 * 17408 + t * 8192, nc >> 6, nc & 63, b_val((nc >> 6) + t, nc & 63));
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) { ptx::mbar_init(afull + 8 * i, 4); ptx::mbar_init(aempty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(afull + 8 * i, 4 * GROUPS); ptx::mbar_init(aempty + 8 * i, 1); }
     ptx::mbar_init(done, 1);
     ptx::fence_mbar_init();
   }
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(160, 1) st_rate_kernel(long long* cycles, int 
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
   } else {
     const int quad = warp & 3, L = quad * 32 + lane;          // TMEM lane = pixel
+    const int group = (warp - 1) >> 2;
     for (int it = 0; it < iters; ++it) {
       const int b = it & 3;
       if (it >= 4) ptx::mbar_wait(aempty + 8 * b, ((it - 4) >> 2) & 1);    // row it-4 (same buffer) has been consumed
@@ -209,16 +211,19 @@ __global__ void __launch_bounds__(160, 1) st_rate_kernel(long long* cycles, int 
       const uint8_t* slot = smem + (it % 3) * 17408;
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
+        if (GROUPS == 3 && dx != group) continue;
         const int p = L + dx;
         uint32_t v[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const uint4 q = *reinterpret_cast<const uint4*>(slot + p * 128 + ((g ^ (p & 7)) << 4));
+          uint4 q = make_uint4(it, lane, g, dx);
+          if (WHAT & 1) q = *reinterpret_cast<const uint4*>(slot + p * 128 + ((g ^ (p & 7)) << 4));
           v[g * 4] = q.x; v[g * 4 + 1] = q.y; v[g * 4 + 2] = q.z; v[g * 4 + 3] = q.w;
         }
-        ptx::tmem_st32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + b * 96 + dx * 32, v);
+        if (WHAT & 2) ptx::tmem_st32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + b * 96 + dx * 32, v);
+        else if (v[0] + v[7] + v[13] + v[31] == 0x12345u) cycles[1] = 0;      // keep the loads alive
       }
-      ptx::tmem_st_wait();
+      if (WHAT & 2) ptx::tmem_st_wait();
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(afull + 8 * b);
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(160, 1) st_rate_kernel(long long* cycles, int 
   __syncthreads();
   ptx::tc_fence_after_sync();
   // check the last accumulator against the scalar reference (rows it-2..it of the last iteration)
-  if (warp >= 1 && bad) {
+  if (warp >= 1 && warp <= 4 && bad && WHAT == 3) {
     const int quad = warp & 3, p = quad * 32 + lane, it = iters - 1;
     for (int h = 0; h < 2; ++h) {
       uint32_t vs[32];
@@ -248,17 +253,17 @@ __global__ void __launch_bounds__(160, 1) st_rate_kernel(long long* cycles, int 
   if (threadIdx.x < 32) ptx::tmem_dealloc(tmem, 512);
 }
 
-void run_st(int grid)
+template <int GROUPS, int WHAT = 3> void run_st(int grid)
 {
   long long* d; cudaMalloc(&d, grid * sizeof(long long));
   int* bad; cudaMalloc(&bad, sizeof(int)); cudaMemset(bad, 0, sizeof(int));
   const int smem = 1024 + 3 * 17408 + 9 * 8192 + 128;
-  cudaFuncSetAttribute(st_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(st_rate_kernel<GROUPS, WHAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 2000;
   for (int rep = 0; rep < 2; ++rep) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a);
-    st_rate_kernel<<<grid, 160, smem>>>(d, iters, bad);
+    st_rate_kernel<GROUPS, WHAT><<<grid, 32 + 128 * GROUPS, smem>>>(d, iters, bad);
     cudaEventRecord(b);
     cudaError_t e = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, a, b);
@@ -266,7 +271,7 @@ void run_st(int grid)
     int hb = 0; cudaMemcpy(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost);
     double cyc = 0; for (int i = 0; i < grid; ++i) cyc += h[i]; cyc /= grid;
     const double mmas = 36.0 * iters;
-    printf("%-44s grid=%3d rep=%d  %s  %.1f cyc/MMA (math 32)  %.3f ms  %.0f TFLOP/s  mismatches %d of %d\n", "N=64 .ts, rows copied by 4 warps (tcgen05.st)", grid, rep,
+    printf("%-44s grid=%3d rep=%d  %s  %.1f cyc/MMA (math 32)  %.3f ms  %.0f TFLOP/s  mismatches %d of %d\n", WHAT == 1 ? "N=64 .ts, 4 warps ld.shared only (no tcgen05.st)" : WHAT == 2 ? "N=64 .ts, 4 warps tcgen05.st only (no ld.shared)" : GROUPS == 1 ? "N=64 .ts, rows copied by 4 warps (tcgen05.st)" : "N=64 .ts, rows copied by 12 warps (tcgen05.st)", grid, rep,
            cudaGetErrorString(e), cyc / mmas, ms, 2.0 * 128 * 64 * 16 * mmas * grid / ms / 1e9, hb, 8192 * grid * (rep + 1));
     if (e != cudaSuccess) break;
   }
@@ -311,7 +316,9 @@ int main()
   run<1>(148, "N=64 .ts (A resident in TMEM)");
   run<2>(148, "N=64 .ts + 12 tcgen05.cp.128x256b per row");
   run<2>(1, "N=64 .ts + copies, single CTA");
-  run_st(148);
-  run_st(1);
+  run_st<1>(148);
+  run_st<3>(148);
+  run_st<1, 1>(148);
+  run_st<1, 2>(148);
   return 0;
 }
