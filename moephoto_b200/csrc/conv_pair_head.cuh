@@ -7,9 +7,11 @@
 //     (M = 256 over the pair, N = 16 = 9 taps padded, K = 64) multiplies it with the head filter:
 //     P_t(Y,X) = <w_head[t], act(Y,X,:)>, fp32 in TMEM;
 //   * four reader warps move P (9 floats per pixel) to a planar fp32 buffer: 36 B per pixel instead of 128 B,
-//     and the 2 x 12.8 GB intermediate tensors of an a4 tile are never written or read; the second branch's
-//     launch adds its P onto the first's, so one array leaves the pair of launches;
-//   * head_stencil_kernel (kernels_simt.cuh) then sums the 3x3 stencil of P_u + P_r, rounds, blends, stores.
+//     and the 2 x 12.8 GB intermediate tensors of an a4 tile are never written or read.  Each branch keeps its
+//     own P array: the reference's half model rounds each head to fp16 BEFORE adding them (models.py:38), so the
+//     two stencil sums must stay apart (round 1 added branch 2 onto branch 1's array — the same HBM traffic, as a
+//     read-modify-write inside this kernel);
+//   * head_stencil_kernel (below) sums the 3x3 stencil of P_u and of P_r, rounds each, adds, rounds, blends, stores.
 // Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader) / weight handshake (peer), 2..9 epilogue,
 // 10 head-MMA issuer (leader), 11..14 P readers.  TMEM: 3 accumulator stages x 128 columns + 2 P stages x 32.
 #pragma once
@@ -21,8 +23,7 @@ namespace moe {
 struct PairHeadParams {
   ConvParams c;            // the convolution (r = 2, EPI_BIAS_PRELU); c.out is unused
   const uint8_t* head_img; // [16 rows][128 B] swizzled fp16: rows 0..8 = the 9 taps of THIS branch's head filter
-  float* pbuf;             // [N][9][2H][2W] fp32
-  int accumulate;          // 1: pbuf += P (second branch adds onto the first: the stencil then reads ONE array)
+  float* pbuf;             // [N][9][2H][2W] fp32, this branch's array
 };
 
 constexpr int kPairHeadThreads = 15 * 32;
@@ -294,18 +295,9 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
         if (x < p.W) {
           // chunk c of this pair's group g is sub-pixel (i, j) = (g, c): output pixel (2y + g, 2x + c)
           float* dst = hp.pbuf + static_cast<size_t>(n) * 9 * plane + static_cast<size_t>(2 * y + g_fixed) * Wo + 2 * x;
-          if (hp.accumulate) {
-            float2 old[9];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) old[t] = *reinterpret_cast<const float2*>(dst + t * plane);
-#pragma unroll
-            for (int t = 0; t < 9; ++t)
-              *reinterpret_cast<float2*>(dst + t * plane) = make_float2(old[t].x + __uint_as_float(v0[t]), old[t].y + __uint_as_float(v1[t]));
-          } else {
-#pragma unroll
-            for (int t = 0; t < 9; ++t)
-              *reinterpret_cast<float2*>(dst + t * plane) = make_float2(__uint_as_float(v0[t]), __uint_as_float(v1[t]));
-          }
+          for (int t = 0; t < 9; ++t)
+            *reinterpret_cast<float2*>(dst + t * plane) = make_float2(__uint_as_float(v0[t]), __uint_as_float(v1[t]));
         }
       }
     }
@@ -321,15 +313,16 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   }
 }
 
-// out(Y,X) = round16( sum_{dy,dx} P[dy*3+dx](Y+dy-1, X+dx-1) ), P = P_u + P_r, zero outside the computed rectangle,
-// then the seam blend and the canvas store of head_blend_kernel / head_tc_kernel.
+// out(Y,X) = round16( round16(S_u) + round16(S_r) ), S_b = sum_{dy,dx} P_b[dy*3+dx](Y+dy-1, X+dx-1), zero outside the
+// computed rectangle, then the seam blend and the canvas store of head_blend_kernel / head_tc_kernel.
 // A thread owns 4 consecutive pixels of a row: per tap plane ONE aligned 16-byte load (two 8-byte loads when the row
 // pitch is not a multiple of 4 floats); the dx = -1 / +1 taps take their fourth value from the neighbouring lane
 // (shuffle; the warp's edge lanes load it).  A block therefore reads 2 KB of contiguous floats per plane row instead of
 // the 1 KB of misaligned 4-byte loads of the one-pixel-per-thread version (3.6 TB/s, profiles/r01_bench_n1_final.json).
 struct HeadStencilParams {
   HeadParams g;            // geometry, seam and canvas (u/r/wu/wr unused)
-  const float* pu;         // [N][9][H][W]: P_u + P_r (the second branch's kernel accumulated onto the first's)
+  const float* pu;         // [N][9][H][W]: P of branch `u`
+  const float* pr;         // same for branch `convt_R1`
 };
 
 constexpr int kStencilThreads = 128;
@@ -342,52 +335,60 @@ __global__ void __launch_bounds__(kStencilThreads) head_stencil_kernel(const Hea
   const int x = (blockIdx.x * kStencilThreads + threadIdx.x) * kStencilPx;
   const int n = blockIdx.z;
   const size_t plane = static_cast<size_t>(g.H) * g.W;
-  const float* bu = p.pu + static_cast<size_t>(n) * 9 * plane;
-  const bool vec4 = (g.W & 3) == 0 && (reinterpret_cast<uintptr_t>(bu) & 15) == 0 && (plane & 3) == 0;   // rows of every plane 16-byte aligned
+  const float* bp[2] = {p.pu + static_cast<size_t>(n) * 9 * plane, p.pr + static_cast<size_t>(n) * 9 * plane};
+  const bool vec4 = (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(bp[0]) | reinterpret_cast<uintptr_t>(bp[1])) & 15) == 0 &&
+                    (plane & 3) == 0;                            // rows of every plane 16-byte aligned
   const int nvalid = min(kStencilPx, g.W - x);       // <= 0: this thread is right of the rectangle (it still shuffles)
   // the whole warp must reach the shuffles: no early return
   for (int y = blockIdx.y; y < g.H; y += gridDim.y) {            // gridDim.y is capped at 65535 rows
     const int cy = g.oy + y;
     const bool row_kept = cy >= g.keep_y0 && cy < g.keep_y1;     // uniform over the block
     if (!row_kept) continue;
-    float acc[3][kStencilPx];                                    // [dy][pixel]: (t(dx=0) + t(dx=1)) + t(dx=2), as head_blend_kernel
+    float head[2][kStencilPx];                                   // the two heads' stencil sums, each rounded to fp16
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int yy = y + dy - 1;
-      const bool in_y = yy >= 0 && yy < g.H;                     // uniform over the block
-      float s[3][kStencilPx];
+    for (int b = 0; b < 2; ++b) {
+      const float* bu = bp[b];
+      float acc[3][kStencilPx];                                  // [dy][pixel]: (t(dx=0) + t(dx=1)) + t(dx=2), as head_blend_kernel
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        float v[kStencilPx] = {0.f, 0.f, 0.f, 0.f};
-        const float* row = bu + static_cast<size_t>(dy * 3 + dx) * plane + static_cast<size_t>(in_y ? yy : 0) * g.W;
-        if (in_y && nvalid > 0) {
-          if (nvalid == kStencilPx && vec4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(row + x));
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-          } else if (nvalid == kStencilPx && ((reinterpret_cast<uintptr_t>(row + x) & 7) == 0)) {
-            const float2 q0 = __ldg(reinterpret_cast<const float2*>(row + x));
-            const float2 q1 = __ldg(reinterpret_cast<const float2*>(row + x + 2));
-            v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
-          } else {
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y + dy - 1;
+        const bool in_y = yy >= 0 && yy < g.H;                   // uniform over the block
+        float s[3][kStencilPx];
 #pragma unroll
-            for (int i = 0; i < kStencilPx; ++i) if (i < nvalid) v[i] = __ldg(row + x + i);
+        for (int dx = 0; dx < 3; ++dx) {
+          float v[kStencilPx] = {0.f, 0.f, 0.f, 0.f};
+          const float* row = bu + static_cast<size_t>(dy * 3 + dx) * plane + static_cast<size_t>(in_y ? yy : 0) * g.W;
+          if (in_y && nvalid > 0) {
+            if (nvalid == kStencilPx && vec4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(row + x));
+              v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else if (nvalid == kStencilPx && ((reinterpret_cast<uintptr_t>(row + x) & 7) == 0)) {
+              const float2 q0 = __ldg(reinterpret_cast<const float2*>(row + x));
+              const float2 q1 = __ldg(reinterpret_cast<const float2*>(row + x + 2));
+              v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+            } else {
+#pragma unroll
+              for (int i = 0; i < kStencilPx; ++i) if (i < nvalid) v[i] = __ldg(row + x + i);
+            }
+          }
+          if (dx == 1) {
+#pragma unroll
+            for (int i = 0; i < kStencilPx; ++i) s[1][i] = v[i];
+          } else if (dx == 0) {                                  // pixel i needs column x + i - 1
+            float left = __shfl_up_sync(0xffffffffu, v[3], 1);
+            if (lane == 0) left = (in_y && nvalid > 0 && x > 0) ? __ldg(row + x - 1) : 0.f;
+            s[0][0] = left; s[0][1] = v[0]; s[0][2] = v[1]; s[0][3] = v[2];
+          } else {                                               // pixel i needs column x + i + 1
+            float right = __shfl_down_sync(0xffffffffu, v[0], 1);
+            if (lane == 31) right = (in_y && x + kStencilPx < g.W) ? __ldg(row + x + kStencilPx) : 0.f;
+            s[2][0] = v[1]; s[2][1] = v[2]; s[2][2] = v[3]; s[2][3] = right;
           }
         }
-        if (dx == 1) {
 #pragma unroll
-          for (int i = 0; i < kStencilPx; ++i) s[1][i] = v[i];
-        } else if (dx == 0) {                                    // pixel i needs column x + i - 1
-          float left = __shfl_up_sync(0xffffffffu, v[3], 1);
-          if (lane == 0) left = (in_y && nvalid > 0 && x > 0) ? __ldg(row + x - 1) : 0.f;
-          s[0][0] = left; s[0][1] = v[0]; s[0][2] = v[1]; s[0][3] = v[2];
-        } else {                                                 // pixel i needs column x + i + 1
-          float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-          if (lane == 31) right = (in_y && x + kStencilPx < g.W) ? __ldg(row + x + kStencilPx) : 0.f;
-          s[2][0] = v[1]; s[2][1] = v[2]; s[2][2] = v[3]; s[2][3] = right;
-        }
+        for (int i = 0; i < kStencilPx; ++i) acc[dy][i] = (s[0][i] + s[1][i]) + s[2][i];
       }
 #pragma unroll
-      for (int i = 0; i < kStencilPx; ++i) acc[dy][i] = (s[0][i] + s[1][i]) + s[2][i];
+      for (int i = 0; i < kStencilPx; ++i) head[b][i] = h_round((acc[0][i] + acc[1][i]) + acc[2][i]);
     }
     if (nvalid <= 0) continue;
     __half* dst = g.canvas + n * g.plane_stride + static_cast<int64_t>(cy) * g.row_stride + (g.ox + x);
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(kStencilThreads) head_stencil_kernel(const Hea
     for (int i = 0; i < kStencilPx; ++i) {
       const int cx = g.ox + x + i;
       keep[i] = i < nvalid && cx >= g.keep_x0 && cx < g.keep_x1;
-      float v = h_round((acc[0][i] + acc[1][i]) + acc[2][i]);
+      float v = h_round(head[0][i] + head[1][i]);               // u + convt_R1(t), models.py:38
       if (keep[i] && (cy < g.blend_y1 || cx < g.blend_x1)) {
         const float old = __half2float(dst[i]);
         if (cy < g.blend_y1) v = h_round(old + h_round(g.ramp[cy - g.ramp_y0] * h_round(v - old)));

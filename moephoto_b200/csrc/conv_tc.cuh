@@ -84,10 +84,17 @@ __device__ __forceinline__ void conv_decode_item(const ConvParams& p, int item, 
   y1 = min(p.H, y0 + p.seg_rows);
 }
 
+__device__ __forceinline__ float h_round(float v) { return __half2float(__float2half_rn(v)); }
+
+// Epilogue arithmetic with the rounding points of the reference's half model: every aten op of
+// models.py rounds its result to fp16 — the convolution (fp32 accumulate, bias inside), PReLU, the ScaleLayer
+// multiply (models.py:73) and the residual add (models.py:60) are separate ops.  Returns the value BEFORE the final
+// rounding of the store (the caller packs with __floats2half2_rn).  Products / sums of two fp16 values are exact
+// in fp32, so rounding them to fp16 afterwards is the single rounding the reference's fp32-opmath kernels do.
 __device__ __forceinline__ float epi_apply(float v, int epi, float param, float bias, float skip) {
-  if (epi == EPI_PRELU) return v >= 0.f ? v : param * v;
-  if (epi == EPI_SCALE_SKIP) return fmaf(v, param, skip);
-  if (epi == EPI_BIAS_PRELU) { v += bias; return v >= 0.f ? v : param * v; }
+  if (epi == EPI_PRELU) { v = h_round(v); return v >= 0.f ? v : param * v; }
+  if (epi == EPI_SCALE_SKIP) return h_round(h_round(v) * param) + skip;
+  if (epi == EPI_BIAS_PRELU) { v = h_round(v + bias); return v >= 0.f ? v : param * v; }
   return v;
 }
 

@@ -266,14 +266,14 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
 
 // ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
 int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, int N, int H, int W,
-                     float slope, const uint8_t* head_img, float* pbuf, int accumulate, int center_only = 0)
+                     float slope, const uint8_t* head_img, float* pbuf, int center_only = 0)
 {
   PairHeadParams hp{};
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
   p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
   p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg;
-  hp.head_img = head_img; hp.pbuf = pbuf; hp.accumulate = accumulate;
+  hp.head_img = head_img; hp.pbuf = pbuf;
   Timed timed(e, st, 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
   const int npairs_max = (e->sm_count / 2) & ~1;
   const int strips1 = (W + kStripW - 1) / kStripW;
@@ -711,13 +711,13 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     // the two upsample stacks: branch 0 on `out`, branch 1 on the trunk           models.py:29-33,125-154; MoeNet_lite2.py:47-50
     const __half* head_in[2] = {bufA, bufT};
     const bool fuse = !e->simt && !e->no_pair && !e->no_fuse && m->n_up >= 1 && m->r == 2 && e->sm_count >= 4;
-    float* pbuf = nullptr;
+    float* pbuf[2] = {nullptr, nullptr};
     if (m->n_up >= 1 && m->r == 2) {
       __half* stage_buf[2] = {reinterpret_cast<__half*>(up0), reinterpret_cast<__half*>(up0 + 4 * unit)};   // S1 (4 units), S2 (16 units)
       uint8_t* fin = up0 + stage_units(m) * unit;
       size_t fin_units = 1;
       for (int i = 0; i < m->n_up; ++i) fin_units *= 4;
-      pbuf = reinterpret_cast<float*>(fin);                        // fused: branch 1 accumulates onto branch 0's P
+      for (int b = 0; b < 2; ++b) pbuf[b] = reinterpret_cast<float*>(fin + b * fin_units * unit);   // fused: one P array per branch (36 of the 128 B per pixel)
       for (int b = 0; b < 2; ++b) {
         const __half* src = b ? bufT : bufA;
         for (int s2 = 0; s2 < m->n_up; ++s2) {
@@ -727,7 +727,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
           const float* wb = m->up_bias[4 * b + s2];
           const float slope = m->scalars[14 + 4 * b + s2];
           if (last && fuse) {
-            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, pbuf, b, one_by_one)) != MOE_OK) return rc;
+            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, pbuf[b], one_by_one)) != MOE_OK) return rc;
           } else {
             __half* dst = last ? reinterpret_cast<__half*>(fin + b * fin_units * unit) : stage_buf[s2];
             if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
@@ -758,10 +758,10 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
     if (fuse) {
       HeadStencilParams sp{};
-      sp.g = hp; sp.pu = pbuf;
+      sp.g = hp; sp.pu = pbuf[0]; sp.pr = pbuf[1];
       dim3 sgrid((hp.W + kStencilThreads * kStencilPx - 1) / (kStencilThreads * kStencilPx), std::min(hp.H, 65535), N);
       if (sgrid.z > 65535u) return fail(MOE_ERR_INVALID, "too many planes for the stencil kernel grid");
-      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (36 + 2));   // bytes: one 9-float read, one fp16 write
+      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (72 + 2));   // bytes: two 9-float reads, one fp16 write
       head_stencil_kernel<<<sgrid, kStencilThreads, 0, st>>>(sp);
     } else if (e->simt) {
       dim3 hgrid((hp.W + 127) / 128, hp.H, N);

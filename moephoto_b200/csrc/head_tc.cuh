@@ -2,8 +2,8 @@
 // and the canvas store (imageProcess.py:164-170) in one bandwidth-bound kernel.
 //
 // A 64->1 3x3 convolution is rewritten as  out(Y,X) = sum_{dy,dx} P_{dy,dx}(Y+dy-1, X+dx-1)  with
-// P_t(y,x) = <w_u[t], U(y,x,:)> + <w_r[t], R(y,x,:)>  — nine 64-long dot products per INPUT pixel and per
-// branch.  The dot products are a GEMM: [128 pixels x 64] x [64 x 16] (9 taps padded to N=16), so the
+// P^b_t(y,x) = <w_b[t], B(y,x,:)>, b = u, r — nine 64-long dot products per INPUT pixel and per branch, kept apart
+// because the reference's half model rounds each head to fp16 before adding them (models.py:38).  The dot products are a GEMM: [128 pixels x 64] x [64 x 16] (9 taps padded to N=16), so the
 // tensor cores produce P from the raw NHWC rows with 8 tcgen05.mma per row (2 branches x 4 K-steps,
 // no shifted views), each activation is read from HBM exactly once, and the 3x3 stencil collapses to
 // 9 fp32 adds per pixel on the CUDA cores: the horizontal part through a small smem exchange, the vertical
@@ -33,7 +33,9 @@ constexpr int kHeadThreads = 192;
 constexpr int kHeadSlots = 5;
 constexpr uint32_t kHeadSlotBytes = 2 * kStageBytes;   // U row + R row
 constexpr int kHeadAccStages = 4;
-constexpr uint32_t kHeadSmemBytes = 1024 + kHeadSlots * kHeadSlotBytes + 4096 + 2 * 9 * 130 * 4 + 1024;
+constexpr uint32_t kHeadExFloats = 2 * 9 * 130;       // one exchange buffer: [branch][tap][130]
+constexpr uint32_t kHeadTmemCols = kHeadAccStages * 32;   // per stage: 16 columns (9 taps used) for each branch
+constexpr uint32_t kHeadSmemBytes = 1024 + kHeadSlots * kHeadSlotBytes + 4096 + 2 * kHeadExFloats * 4 + 1024;
 
 __device__ __forceinline__ void head_decode_item(const HeadTcParams& p, int item, int& n, int& xl, int& y0, int& y1) {
   const int seg = item % p.nseg;
@@ -55,8 +57,8 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t ring = base;
   const uint32_t wsm = ring + S * kHeadSlotBytes;          // 4 KB of weights
-  const uint32_t exs = wsm + 4096;                         // exchange buffers [2][9][130] float
-  const uint32_t bars = exs + 2 * 9 * 130 * 4;
+  const uint32_t exs = wsm + 4096;                         // exchange buffers [2][2 branches][9][130] float
+  const uint32_t bars = exs + 2 * kHeadExFloats * 4;
   const uint32_t barsa = (bars + 7u) & ~7u;
   const uint32_t full = barsa, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
   const uint32_t wbar = tempty + 8 * AS, tslot = wbar + 8;
@@ -73,7 +75,7 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
     ptx::prefetch_tmap(&maps.u);
     ptx::prefetch_tmap(&maps.r);
   }
-  if (warp == 1) ptx::tmem_alloc(tslot, 64);
+  if (warp == 1) ptx::tmem_alloc(tslot, kHeadTmemCols);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -122,7 +124,7 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
           for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::mma_f16_ss(tmem_base + stage * 16, arow + (b * (kStageBytes >> 4) + k * 2), bdesc0 + (b * 128 + k * 2), idesc, (b | k) != 0);
+              ptx::mma_f16_ss(tmem_base + stage * 32 + b * 16, arow + (b * (kStageBytes >> 4) + k * 2), bdesc0 + (b * 128 + k * 2), idesc, k != 0);
           ptx::mma_commit(tfull + 8 * stage);
           ptx::mma_commit(empty + 8 * slot);
         }
@@ -143,31 +145,40 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
       const int X = xl + L;                          // column within the computed rectangle
       const int cx = g.ox + X;
       const bool col_ok = L >= 1 && L <= kHeadStripOut && X < g.W && cx >= g.keep_x0 && cx < g.keep_x1;
-      float acc_a = 0.f, prev_h0 = 0.f;
+      float acc_a[2] = {0.f, 0.f}, prev_h0[2] = {0.f, 0.f};
       for (int yy = y0 - 1; yy <= y1; ++yy, ++ld) {
         const uint32_t stage = ld % AS;
         ptx::mbar_wait(tfull + 8 * stage, (ld / AS) & 1);
         ptx::tc_fence_after_sync();
-        uint32_t v[16];
-        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 16, v);
+        uint32_t v[2][16];
+        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 32, v[0]);
+        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 32 + 16, v[1]);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(tempty + 8 * stage);
-        float* eb = ex + (ld & 1) * (9 * 130);
+        float* eb = ex + (ld & 1) * kHeadExFloats;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) eb[t * 130 + L + 1] = __uint_as_float(v[t]);
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) eb[(b * 9 + t) * 130 + L + 1] = __uint_as_float(v[b][t]);
         ptx::named_bar_sync(1, 128);
-        float h[3];
+        float outv[2];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-          h[dy] = (eb[(dy * 3 + 0) * 130 + L] + eb[(dy * 3 + 1) * 130 + L + 1]) + eb[(dy * 3 + 2) * 130 + L + 2];
-        const float outv = acc_a + h[2];             // row yy-1 is complete: h0(yy-2) + h1(yy-1) + h2(yy)
-        acc_a = prev_h0 + h[1];
-        prev_h0 = h[0];
+        for (int b = 0; b < 2; ++b) {
+          const float* e2 = eb + b * 9 * 130;
+          float h[3];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+            h[dy] = (e2[(dy * 3 + 0) * 130 + L] + e2[(dy * 3 + 1) * 130 + L + 1]) + e2[(dy * 3 + 2) * 130 + L + 2];
+          outv[b] = acc_a[b] + h[2];                 // row yy-1 is complete: h0(yy-2) + h1(yy-1) + h2(yy)
+          acc_a[b] = prev_h0[b] + h[1];
+          prev_h0[b] = h[0];
+        }
         const int Y = yy - 1;
         const int cy = g.oy + Y;
         if (col_ok && Y >= y0 && cy >= g.keep_y0 && cy < g.keep_y1) {
-          float val = h_round(outv);
+          // each head is an fp16 tensor in the reference's half model, their sum a third op (models.py:38)
+          float val = h_round(h_round(outv[0]) + h_round(outv[1]));
           __half* dst = g.canvas + n * g.plane_stride + static_cast<int64_t>(cy) * g.row_stride + cx;
           if (cy < g.blend_y1 || cx < g.blend_x1) {
             const float old = __half2float(*dst);
@@ -184,7 +195,7 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, 64);
+    ptx::tmem_dealloc(tmem_base, kHeadTmemCols);
   }
 }
 

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const FirstParams p, in
         uint32_t w[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float f0 = a[2 * c], f1 = a[2 * c + 1];
+          float f0 = h_round(a[2 * c]), f1 = h_round(a[2 * c + 1]);      // conv2d and prelu are two aten ops: two roundings
           f0 = f0 >= 0.f ? f0 : p.slope * f0;
           f1 = f1 >= 0.f ? f1 : p.slope * f1;
           const __half2 hv = __floats2half2_rn(f0, f1);
@@ -127,8 +127,6 @@ struct HeadParams {
   int64_t plane_stride, row_stride;
 };
 
-__device__ __forceinline__ float h_round(float v) { return __half2float(__float2half_rn(v)); }
-
 // Conv3x3(F,1)(u) + Conv3x3(F,1)(r), rounded to fp16, seam-blended against what the canvas holds and
 // stored.  One thread per output pixel.
 __global__ void __launch_bounds__(128) head_blend_kernel(const HeadParams p)
@@ -142,9 +140,10 @@ __global__ void __launch_bounds__(128) head_blend_kernel(const HeadParams p)
   if (x >= p.W) return;
   const int cy = p.oy + y, cx = p.ox + x;
   if (cy < p.keep_y0 || cy >= p.keep_y1 || cx < p.keep_x0 || cx >= p.keep_x1) return;
-  float acc = 0.f;
+  float head[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int b = 0; b < 2; ++b) {
+    float acc = 0.f;
     const __half* src = b ? p.r : p.u;
     const float* wb = ws + b * 576;
 #pragma unroll 1
@@ -170,8 +169,9 @@ __global__ void __launch_bounds__(128) head_blend_kernel(const HeadParams p)
         }
       }
     }
+    head[b] = h_round(acc);
   }
-  float v = h_round(acc);
+  float v = h_round(head[0] + head[1]);              // u + convt_R1(t): each head is an fp16 tensor, the add a third op
   __half* dst = p.canvas + n * p.plane_stride + cy * p.row_stride + cx;
   if (cy < p.blend_y1 || cx < p.blend_x1) {
     const float old = __half2float(*dst);
@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(const ConvParams p)
 }
 
 // ---- FRM, the feature recalibration module of MoeNet_lite2 (models.py:270-287; used by LB, MoeNet_lite2.py:15-19):
-// t <- v * sigmoid(W1 relu(W0 mean_hw(v) + b0) + b1) + t.  The mean is over the whole reference tile, so the
+// t <- v * sigmoid(W1 relu(W0 mean_hw(v) + b0) + b1) + t, every op rounded to fp16 as in the reference's half model.
+// The mean is over the whole reference tile, so the
 // reduction is two deterministic passes (fixed chunking, fixed summation order: the result is reproducible).
 constexpr int kFrmBlocks = 512;                    // partial sums per plane
 
@@ -279,19 +280,19 @@ __global__ void __launch_bounds__(64) frm_gate_kernel(const float* partial, cons
   const int n = blockIdx.x, c = threadIdx.x;
   float s = 0.f;
   for (int b = 0; b < kFrmBlocks; ++b) s += partial[(static_cast<size_t>(n) * kFrmBlocks + b) * 64 + c];
-  mean[c] = s * inv_pixels;
+  mean[c] = h_round(s * inv_pixels);          // adaptive_avg_pool2d of a half tensor: fp32 accumulation, fp16 result
   __syncthreads();
   if (c < 3) {
     float h = frm[192 + c];
     for (int k = 0; k < 64; ++k) h += frm[c * 64 + k] * mean[k];
-    hid[c] = fmaxf(h, 0.f);
+    hid[c] = fmaxf(h_round(h), 0.f);          // conv_du.0 (+ bias) rounds, ReLU is exact
   }
   __syncthreads();
-  const float z = frm[452 + c] + frm[196 + c * 4] * hid[0] + frm[196 + c * 4 + 1] * hid[1] + frm[196 + c * 4 + 2] * hid[2];
-  gate[n * 64 + c] = 1.f / (1.f + expf(-z));
+  const float z = h_round(frm[452 + c] + frm[196 + c * 4] * hid[0] + frm[196 + c * 4 + 1] * hid[1] + frm[196 + c * 4 + 2] * hid[2]);   // conv_du.2
+  gate[n * 64 + c] = h_round(1.f / (1.f + expf(-z)));                                                                               // Sigmoid
 }
 
-// t = round16(v * gate + t), NHWC, 8 channels per thread
+// t = round16(round16(v * gate) + t), NHWC, 8 channels per thread
 __global__ void __launch_bounds__(256) frm_apply_kernel(const __half* v, __half* t, const float* gate, int64_t pixels_per_plane, int planes)
 {
   const int64_t total = pixels_per_plane * planes * 8;
@@ -308,7 +309,8 @@ __global__ void __launch_bounds__(256) frm_apply_kernel(const __half* v, __half*
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 fv = __half22float2(hv[e]), ft = __half22float2(ht[e]);
-      ht[e] = __floats2half2_rn(__fadd_rn(__fmul_rn(fv.x, gg[2 * e]), ft.x), __fadd_rn(__fmul_rn(fv.y, gg[2 * e + 1]), ft.y));
+      // x * y (models.py:287) and + x (MoeNet_lite2.py:19) are two aten ops on half tensors: two roundings
+      ht[e] = __floats2half2_rn(__fadd_rn(h_round(__fmul_rn(fv.x, gg[2 * e])), ft.x), __fadd_rn(h_round(__fmul_rn(fv.y, gg[2 * e + 1])), ft.y));
     }
     reinterpret_cast<uint4*>(t)[i] = qt;
   }

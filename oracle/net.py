@@ -16,11 +16,17 @@ Pinning: tests/test_oracle_vs_reference.py runs this against the unmodified refe
 the build container through oracle/refharness.py) and against tests/golden/*.npz generated from it
 (the reference has no golden vectors of its own — SURVEY.md §4 — so parity is pinned by running it).
 
-Two arithmetic modes:
+Three arithmetic modes:
   mode='fp32'  : the reference's CPU path (fp32 everywhere).
-  mode='f16io' : the rounding points of the CUDA engine (and, up to two extra roundings in the ARSB
-                 tail, of the reference's GPU fp16 path): weights and every stored activation are
-                 rounded to IEEE fp16, accumulation stays fp32.  See DESIGN.md §numerics.
+  mode='ref16' : the reference's GPU path, `model.half()` on half tensors (imageProcess.py:309-318): EVERY aten
+                 op rounds its result to IEEE fp16 — conv (fp32 accumulate, one rounding, bias inside), prelu,
+                 the ScaleLayer multiply (models.py:73), the residual add (models.py:60), the branch add
+                 (models.py:38), and in MoeNet_lite2 the pooled mean, both 1x1 convs of FRM, the sigmoid, the
+                 gate multiply and the skip add (models.py:282-287, MoeNet_lite2.py:15-19).  This is the CUDA
+                 engine's numerics contract.  Pinned against the UNMODIFIED reference run in
+                 half on CPU (tests/test_oracle_vs_reference.py::test_ref16_*; goldens `<case>.ref16`).
+  mode='f16io' : round-1 contract, kept for comparison: fp16 storage with ONE rounding per stored tensor
+                 (the ARSB tail and the branch sum round once where the reference rounds three times).
 Two conv back-ends: 'c' (conv_ref.c, independent of torch) and 'torch' (F.conv2d on CPU = oneDNN,
 the arithmetic the reference's CPU path really executes; used for the timed CPU baseline).
 """
@@ -112,89 +118,126 @@ def conv1x1(x, w, b=None):
   return (y if b is None else y + np.asarray(b, dtype=np.float32)[None, :, None, None]).astype(np.float32)
 
 
+def _modes(sd, mode):
+  """(q, W, S, half): q rounds a stored tensor, W fetches a parameter as the model holds it, S a scalar parameter,
+  half = every aten op rounds (mode 'ref16')"""
+  if mode not in ('fp32', 'f16io', 'ref16'):
+    raise ValueError('unknown oracle mode %r' % (mode,))
+  lowp = mode != 'fp32'
+  q = _q16 if lowp else (lambda a: a)
+  W = (lambda k: _q16(sd[k])) if lowp else (lambda k: sd[k])
+  S = lambda k: np.float32(W(k).reshape(-1)[0])
+  return q, W, S, mode == 'ref16'
+
+
 def forward_lite(sd, x, mode='fp32', backend='c'):
   """MoeNet_lite2.Net.forward (MoeNet_lite2.py:42-54) with LB (:7-20) and FRM (models.py:270-287):
   out = PReLU(conv1x1(x)); t = conv1x1(out); three times t = FRM(conv3x3(PReLU(conv3x3(t)))) + t with
   FRM(v) = v * sigmoid(W1 relu(W0 mean_hw(v) + b0) + b1); res = ures(t), im = uim(out) (each stage:
   PReLU(PixelShuffle2(conv1x1 + bias))); y = conv1x1(res) + conv1x1(im).
-  mode 'f16io' has the CUDA engine's rounding points: every stored tensor fp16, the FRM mean / gate in fp32."""
-  q = _q16 if mode == 'f16io' else (lambda a: a)
-  W = (lambda k: _q16(sd[k])) if mode == 'f16io' else (lambda k: sd[k])
-  S = lambda k: np.float32(W(k).reshape(-1)[0])
+  mode 'ref16': every op of the list above rounds to fp16 (the half model on half tensors).
+  mode 'f16io': every stored tensor fp16, the FRM mean / gate in fp32 (round-1 contract)."""
+  q, W, S, half = _modes(sd, mode)
+  qh = q if half else (lambda a: a)                     # roundings only the reference's per-op path has
   x = np.ascontiguousarray(x, dtype=np.float32)
-  out = q(prelu(conv1x1(x, W('conv_input.weight')), S('relu.weight')))
+  out = q(prelu(qh(conv1x1(x, W('conv_input.weight'))), S('relu.weight')))
   t = q(conv1x1(out, W('conv_input2.weight')))
   for name in ('convt_F11', 'convt_F12', 'convt_F13'):
-    mid = q(prelu(conv3x3(t, W(name + '.conv_1.weight'), None, backend), S(name + '.relu.weight')))
+    mid = q(prelu(qh(conv3x3(t, W(name + '.conv_1.weight'), None, backend)), S(name + '.relu.weight')))
     v = q(conv3x3(mid, W(name + '.conv_2.weight'), None, backend))
-    m = v.mean(axis=(2, 3), dtype=np.float32)                                                   # (N,48)
-    hid = np.maximum(m @ W(name + '.se.conv_du.0.weight').reshape(3, 48).T + W(name + '.se.conv_du.0.bias'), 0)
-    gate = 1.0 / (1.0 + np.exp(-(hid @ W(name + '.se.conv_du.2.weight').reshape(48, 3).T + W(name + '.se.conv_du.2.bias'))))
-    t = q(v * gate.astype(np.float32)[:, :, None, None] + t)
+    m = qh(v.mean(axis=(2, 3), dtype=np.float32))                                                # (N,48) adaptive_avg_pool2d
+    hid = np.maximum(qh((m @ W(name + '.se.conv_du.0.weight').reshape(3, 48).T + W(name + '.se.conv_du.0.bias')).astype(np.float32)), 0)
+    z = qh((hid @ W(name + '.se.conv_du.2.weight').reshape(48, 3).T + W(name + '.se.conv_du.2.bias')).astype(np.float32))
+    gate = qh((1.0 / (1.0 + np.exp(-z.astype(np.float32)))).astype(np.float32))
+    g4 = gate.astype(np.float32)[:, :, None, None]
+    t = q(qh(v * g4) + t) if half else q(v * g4 + t)
   stages = len([k for k in sd if k.startswith('ures.') and k.endswith('.0.weight')])
 
   def branch(a, name):
     for j in range(stages):
-      a = conv1x1(a, W('%s.%d.0.weight' % (name, j)), W('%s.%d.0.bias' % (name, j)))
+      a = qh(conv1x1(a, W('%s.%d.0.weight' % (name, j)), W('%s.%d.0.bias' % (name, j))))
       a = q(prelu(pixel_shuffle(a, 2), S('%s.%d.2.weight' % (name, j))))
     return a
-  y = conv1x1(branch(t, 'ures'), W('convt_R1.weight')) + conv1x1(branch(out, 'uim'), W('convt_I1.weight'))
+  y = qh(conv1x1(branch(t, 'ures'), W('convt_R1.weight'))) + qh(conv1x1(branch(out, 'uim'), W('convt_I1.weight')))
   return q(y)
 
 
 def forward(sd, x, mode='fp32', backend='c'):
-  """x: (N,1,h,w) float32 (values already representable in fp16 for mode='f16io').
+  """x: (N,1,h,w) float32 (values already representable in fp16 for the fp16 modes).
   Returns (N,1,s*h,s*w) float32 — the last element of MyNet.forward's list (imageProcess.py:391-395)."""
   arch = arch_of_state_dict(sd)
   if arch == 'lite':
     return forward_lite(sd, x, mode, backend)
   _, ups = ARCH[arch]
-  q = _q16 if mode == 'f16io' else (lambda a: a)
-  W = (lambda k: _q16(sd[k])) if mode == 'f16io' else (lambda k: sd[k])
-  S = lambda k: np.float32(W(k).reshape(-1)[0])
+  q, W, S, half = _modes(sd, mode)
+  qh = q if half else (lambda a: a)
   cv = lambda a, k, b=None: conv3x3(a, W(k), None if b is None else W(b), backend)
 
   x = np.ascontiguousarray(x, dtype=np.float32)
-  out = q(prelu(cv(x, 'conv_input.weight'), S('relu.weight')))           # models.py:118
+  out = q(prelu(qh(cv(x, 'conv_input.weight')), S('relu.weight')))       # models.py:118
   t = q(cv(out, 'conv_input2.weight'))                                    # models.py:119
   for i in range(1, 7):                                                   # models.py:41-43, 76-80
     p = 'convt_F%d.0.' % i
-    mid = q(prelu(cv(t, p + 'conv_1.weight'), S(p + 'relu.weight')))
-    t = q(t + S(p + 'scale.scale') * cv(mid, p + 'conv_2.weight'))
+    mid = q(prelu(qh(cv(t, p + 'conv_1.weight')), S(p + 'relu.weight')))
+    c2 = cv(mid, p + 'conv_2.weight')
+    if half:
+      t = q(q(q(c2) * S(p + 'scale.scale')) + t)                          # conv, ScaleLayer (:73), Residual (:60): three ops
+    else:
+      t = q(t + S(p + 'scale.scale') * c2)
 
   def branch(a, name):
     for j, r in enumerate(ups):                                           # models.py:29-33
-      a = cv(a, '%s.%d.0.weight' % (name, j), '%s.%d.0.bias' % (name, j))
+      a = qh(cv(a, '%s.%d.0.weight' % (name, j), '%s.%d.0.bias' % (name, j)))
       a = q(prelu(pixel_shuffle(a, r), S('%s.%d.2.weight' % (name, j))))
     hk = ('%s.%d.weight' % (name, len(ups))) if ups else (name + '.weight')
-    return cv(a, hk)                                                      # Conv3x3(F,1)
+    return qh(cv(a, hk))                                                  # Conv3x3(F,1)
 
   y = branch(out, 'u') + branch(t, 'convt_R1')                            # models.py:38,121-123
   return q(y)
 
 
-def forward_torch(sd, x):
-  """The same forward, fp32, entirely in PyTorch CPU functional ops (conv2d / pixel_shuffle / prelu) —
-  operation for operation what the reference's nn.Modules execute on its CPU path (oneDNN), without
-  numpy glue.  Used for the timed CPU baseline (bench.py) and cross-checked against forward() in
-  tests/test_oracle_golden.py.  x: (N,1,h,w) float32 ndarray or tensor -> ndarray."""
+def forward_torch(sd, x, dtype='float32', device='cpu'):
+  """The same forward entirely in PyTorch functional ops (conv2d / pixel_shuffle / prelu / adaptive_avg_pool2d) —
+  operation for operation what the reference's nn.Modules execute, without numpy glue:
+    dtype='float32', device='cpu'  : the reference's CPU path (oneDNN) — the timed CPU baseline of bench.py;
+    dtype='float16', device='cuda' : the reference's GPU path (cuDNN half, every op rounding to fp16) — used on the GPU
+                                     box, where /root/reference does not exist, to measure how far the reference's own
+                                     GPU arithmetic is from its CPU-executed fp16 goldens (tests/test_gpu_engine.py).
+  Cross-checked against forward() in tests/test_oracle_golden.py.  x: (N,1,h,w) ndarray or tensor -> float32 ndarray."""
   import torch
   import torch.nn.functional as F
-  T = lambda k: torch.from_numpy(np.ascontiguousarray(sd[k], dtype=np.float32))
-  if arch_of_state_dict(sd) == 'lite':
-    raise NotImplementedError('forward_torch covers the Net2x/3x/4x/NetDN baselines only')
-  _, ups = ARCH[arch_of_state_dict(sd)]
+  dt = getattr(torch, dtype)
+  T = lambda k: torch.from_numpy(np.ascontiguousarray(sd[k], dtype=np.float32)).to(device=device, dtype=dt)
+  arch = arch_of_state_dict(sd)
   with torch.no_grad():
-    x = torch.as_tensor(np.asarray(x, dtype=np.float32)) if not torch.is_tensor(x) else x
+    x = (torch.as_tensor(np.asarray(x, dtype=np.float32)) if not torch.is_tensor(x) else x).to(device=device, dtype=dt)
+    if arch == 'lite':                                                      # MoeNet_lite2.py:42-54
+      c1 = lambda a, k, b=None: F.conv2d(a, T(k), None if b is None else T(b))
+      c3 = lambda a, k: F.conv2d(a, T(k), None, padding=1)
+      out = F.prelu(c1(x, 'conv_input.weight'), T('relu.weight'))
+      t = c1(out, 'conv_input2.weight')
+      for name in ('convt_F11', 'convt_F12', 'convt_F13'):
+        v = c3(F.prelu(c3(t, name + '.conv_1.weight'), T(name + '.relu.weight')), name + '.conv_2.weight')
+        y = F.adaptive_avg_pool2d(v, 1)
+        y = torch.sigmoid(c1(F.relu(c1(y, name + '.se.conv_du.0.weight', name + '.se.conv_du.0.bias')), name + '.se.conv_du.2.weight', name + '.se.conv_du.2.bias'))
+        t = v * y + t
+      stages = len([k for k in sd if k.startswith('ures.') and k.endswith('.0.weight')])
+
+      def lbranch(a, name):
+        for j in range(stages):
+          a = F.prelu(F.pixel_shuffle(c1(a, '%s.%d.0.weight' % (name, j), '%s.%d.0.bias' % (name, j)), 2), T('%s.%d.2.weight' % (name, j)))
+        return a
+      return (c1(lbranch(t, 'ures'), 'convt_R1.weight') + c1(lbranch(out, 'uim'), 'convt_I1.weight')).float().cpu().numpy()
+    _, ups = ARCH[arch]
     cv = lambda a, k, b=None: F.conv2d(a, T(k), None if b is None else T(b), padding=1)
     out = F.prelu(cv(x, 'conv_input.weight'), T('relu.weight'))
     t = cv(out, 'conv_input2.weight')
     for i in range(1, 7):
       p = 'convt_F%d.0.' % i
-      t = t + T(p + 'scale.scale') * cv(F.prelu(cv(t, p + 'conv_1.weight'), T(p + 'relu.weight')), p + 'conv_2.weight')
+      t = cv(F.prelu(cv(t, p + 'conv_1.weight'), T(p + 'relu.weight')), p + 'conv_2.weight') * T(p + 'scale.scale') + t
 
     def branch(a, name):
       for j, r in enumerate(ups):
         a = F.prelu(F.pixel_shuffle(cv(a, '%s.%d.0.weight' % (name, j), '%s.%d.0.bias' % (name, j)), r), T('%s.%d.2.weight' % (name, j)))
       return cv(a, ('%s.%d.weight' % (name, len(ups))) if ups else (name + '.weight'))
-    return (branch(out, 'u') + branch(t, 'convt_R1')).numpy()
+    return (branch(out, 'u') + branch(t, 'convt_R1')).float().cpu().numpy()

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE — not product code.
 
-Imports the UNMODIFIED reference (/root/reference/python) on CPU fp32 through five
-harness-side shims so that golden vectors can be generated and the
+Imports the UNMODIFIED reference (/root/reference/python) on CPU (fp32, or half through
+`gpu_fp16_config`) through five harness-side shims so that golden vectors can be generated and the
 oracle restatement can be pinned against the real thing.  /root/reference exists only
 in the build container: everything here degrades to `available() == False` elsewhere
 (the GPU box), and nothing in `-m gpu` tests, smoke() or bench.py depends on it.
@@ -70,24 +70,56 @@ def load():
   return _state
 
 
-def run_sr(x, scale, crop=0, model='a', ensemble=0):
-  """reference runSR.sr(getOpt(...))(x) on CPU fp32; returns (y, plan list, opt)."""
+class gpu_fp16_config:
+  """Context manager: make the unmodified reference behave as on its GPU fp16 path while executing on CPU —
+  config.dtype() -> torch.half (so castModel does model.half(), imageProcess.py:309-318, and the blend ramp is
+  evaluated in half, :109) and config.getRunType() -> 2 (the GPU fp16 row of ramCoef, runSR.py:9 / runDN.py:9, so the
+  tile plan is the one a GPU run makes).  Every aten op then rounds to fp16 exactly as on the GPU; only the fp32
+  summation order inside conv2d differs from cuDNN's.  Harness-side instance attributes; zero edits to the reference."""
+
+  def __init__(self, enable=True):
+    self.enable = enable
+
+  def __enter__(self):
+    if self.enable:
+      import torch
+      cfg = load()['config']
+      cfg.dtype = lambda: torch.half
+      cfg.getRunType = lambda: 2
+    return self
+
+  def __exit__(self, *exc):
+    if self.enable:
+      cfg = load()['config']
+      for name in ('dtype', 'getRunType'):
+        if name in vars(cfg):
+          delattr(cfg, name)
+      # castModel casts the CACHED module in place (imageProcess.py:311-318): after a half run its weights stay
+      # rounded to fp16 even when cast back to float.  Drop the cache so a later fp32 call reloads the checkpoint.
+      load()['imageProcess'].modelCache.clear()
+    return False
+
+
+def run_sr(x, scale, crop=0, model='a', ensemble=0, half=False):
+  """reference runSR.sr(getOpt(...))(x) on CPU, fp32 or (half=True) as its GPU fp16 path; returns (y, plan list, opt)."""
   import torch
   ref = load()
   ref['config'].crop_sr = crop if crop else 'auto'
-  opt = ref['runSR'].getOpt({'model': model, 'scale': scale, 'ensemble': ensemble})
-  with torch.no_grad():
-    y = ref['runSR'].sr(opt)(x)
+  with gpu_fp16_config(half):
+    opt = ref['runSR'].getOpt({'model': model, 'scale': scale, 'ensemble': ensemble})
+    with torch.no_grad():
+      y = ref['runSR'].sr(opt)(x.half() if half else x)
   return y, list(opt.iterClip()), opt
 
 
-def run_dn(x, model='lite15', crop=0, strength=1.0):
+def run_dn(x, model='lite15', crop=0, strength=1.0, half=False):
   import torch
   ref = load()
   ref['config'].crop_dn = crop if crop else 'auto'
-  opt = ref['runDN'].getOpt({'model': model, 'strength': strength})
-  with torch.no_grad():
-    y = ref['imageProcess'].RGBFilter(opt)(x)
+  with gpu_fp16_config(half):
+    opt = ref['runDN'].getOpt({'model': model, 'strength': strength})
+    with torch.no_grad():
+      y = ref['imageProcess'].RGBFilter(opt)(x.half() if half else x)
   return y, list(opt.iterClip()), opt
 
 

@@ -10,6 +10,7 @@ around the network:
   blend                      imageProcess.py:120-131
   doCrop                     imageProcess.py:157-172
   _RGBFilter / strengthOp    imageProcess.py:370-377, :562
+  ensemble (+ runSR.sr)      imageProcess.py:558-572, runSR.py:26
   toTorch / toFloat+toOutput imageProcess.py:259-263, :238-257
 Pinned against the unmodified reference by tests/test_oracle_vs_reference.py (tile lists compared
 tuple-for-tuple over a sweep of shapes, stitched output compared bit-for-bit with an identity "net").
@@ -166,6 +167,28 @@ def do_crop(net, x, plan, dtype=np.float32, ramp=None):
     hh, ww = r2.shape[-2:]
     canvas[..., bsc - hh:bsc, rsc - ww:rsc] = r2
   return canvas
+
+
+# the seven dihedral passes of the test-time ensemble (imageProcess.py:564-568): pass k applies FWD[k] to the image,
+# doCrop on the plan of that orientation (`which`: the transposed plan where the pass swaps H and W), then INV[k]
+_t = lambda a: np.swapaxes(a, -1, -2)
+_fx = lambda a: a[..., ::-1]
+_fxy = lambda a: a[..., ::-1, ::-1]
+_seq = lambda *fs: (lambda a: [a := f(a) for f in fs][-1])
+ENSEMBLE_FWD = [_t, _fx, _fxy, _seq(_fx, _t), _seq(_t, _fx), _seq(_t, _fx, _t), _seq(_fxy, _t)]
+ENSEMBLE_INV = [_t, _fx, _fxy, ENSEMBLE_FWD[4], ENSEMBLE_FWD[3], ENSEMBLE_FWD[5], ENSEMBLE_FWD[6]]
+ENSEMBLE_TRANSPOSED = [True, False, False, True, True, False, True]
+
+
+def ensemble(net, x, plan, plan_t, k, dtype=np.float32, ramp=None):
+  """runSR.sr (runSR.py:26) over imageProcess.ensemble (:569-572): (doCrop(x) + sum of the first k dihedral passes)
+  / (k + 1), every add and the division rounded to `dtype`.  plan_t: the plan of the transposed image (:142-152)."""
+  q = (lambda a: a.astype(dtype)) if dtype != np.float32 else (lambda a: a)
+  total = do_crop(net, x, plan, dtype, ramp)
+  for fwd, inv, tr in list(zip(ENSEMBLE_FWD, ENSEMBLE_INV, ENSEMBLE_TRANSPOSED))[:k]:
+    y = do_crop(net, np.ascontiguousarray(fwd(x)), plan_t if tr else plan, dtype, ramp)
+    total = q(total.astype(np.float32) + inv(y).astype(np.float32))
+  return q(total.astype(np.float32) / np.float32(k + 1)) if k else total
 
 
 def rgb_filter(net, img, plan, strength=1.0, dtype=np.float32):

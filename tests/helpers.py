@@ -12,6 +12,7 @@ if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 _cases = None
+_bands = None
 WEIGHT_OF = {('sr', 2): 'a2', ('sr', 3): 'a3', ('sr', 4): 'a4', ('dn', 'lite15'): 'dn_lite15', ('dn', 'lite5'): 'dn_lite5'}
 
 
@@ -33,9 +34,43 @@ def load_case(name):
   c = dict(meta[name])
   c['name'] = name
   c['img'] = z[name + '.img']
-  c['ref'] = z[name + '.ref']
+  c['ref'] = z[name + '.ref']                                  # the reference's fp32 CPU output
+  c['ref16'] = z[name + '.ref16'].astype(np.float32)           # the reference in its GPU fp16 configuration (executed on CPU)
   c['alpha'] = z[name + '.alpha'] if (name + '.alpha') in z.files else None
-  c['weights'] = ('lite%d' % c['arg']) if c.get('model') == 'lite' else WEIGHT_OF[(c['kind'], c['arg'])]
+  c['weights'] = _weights_key(c)
+  return c
+
+
+def _weights_key(c):
+  if c.get('model') == 'lite':
+    return 'lite%d' % c['arg']
+  if c.get('model') == 'p':
+    return 'p%d' % c['arg']
+  return WEIGHT_OF[(c['kind'], c['arg'])]
+
+
+def band_case_names():
+  return list(_load_bands()[1].keys())
+
+
+def _load_bands():
+  global _bands
+  if _bands is None:
+    z = np.load(os.path.join(GOLD, 'bands.npz'))
+    _bands = (z, json.loads(bytes(z['meta']).decode()))
+  return _bands
+
+
+def load_band_case(name):
+  """large golden: the image, the tile list and `windows` = [((y0,y1,x0,x1), fp16-configuration reference output there)]"""
+  z, meta = _load_bands()
+  c = dict(meta[name])
+  c['name'] = name
+  c['img'] = z[name + '.img']
+  c['alpha'] = None
+  c['ensemble'] = 0
+  c['weights'] = _weights_key(c)
+  c['windows'] = [(tuple(w), z['%s.win%d' % (name, i)].astype(np.float32)) for i, w in enumerate(c['windows'])]
   return c
 
 
@@ -52,10 +87,12 @@ def case_input(c, dtype=np.float32):
   return x
 
 
-def oracle_plan(c, planes=3):
+def oracle_plan(c, planes=3, transposed=False):
   from oracle import tiling as T
   h, w = c['img'].shape[:2]
-  return T.make_plan((planes, h, w), c['ram'], c['ram_coef'], c['pad'], c['scale'], 8, c['crop'])
+  if transposed:
+    h, w = w, h
+  return T.make_plan((planes, h, w), c['ram'], c.get('ram_coef', c.get('ram_coef_gpu')), c['pad'], c['scale'], 8, c['crop'])
 
 
 def run_case_oracle(c, mode='fp32', backend='c'):
@@ -66,6 +103,8 @@ def run_case_oracle(c, mode='fp32', backend='c'):
   plan = oracle_plan(c)
   net = lambda a: N.forward(sd, a, mode=mode, backend=backend)
   if c['kind'] == 'sr':
+    if c.get('ensemble', 0):
+      return T.ensemble(net, x, plan, oracle_plan(c, transposed=True), c['ensemble'], dt).astype(np.float32)
     return T.do_crop(net, x, plan, dt).astype(np.float32)
   return T.rgb_filter(net, x, plan, 1.0, dt).astype(np.float32)
 
@@ -83,7 +122,7 @@ def run_case_engine(c):
   try:
     if c['kind'] == 'sr':
       config.crop_sr = c['crop'] if c['crop'] else 'auto'
-      opt = runSR.getOpt({'model': c.get('model', 'a'), 'scale': c['arg']}, weights=sd)
+      opt = runSR.getOpt({'model': c.get('model', 'a'), 'scale': c['arg'], 'ensemble': c.get('ensemble', 0)}, weights=sd)
       y = runSR.sr(opt)(x)
     else:
       config.crop_dn = c['crop'] if c['crop'] else 'auto'
@@ -98,3 +137,22 @@ def run_case_engine(c):
 
 def psnr(a, b):
   return 10 * np.log10(1.0 / max(float(np.mean((a.astype(np.float64) - b) ** 2)), 1e-20))
+
+
+def is_white_noise(c):
+  return c['name'].endswith('_rand')
+
+
+def assert_ref16_bar(y, c, ref=None, what='output'):
+  """THE parity bar against the reference's fp16-configuration output (tests/test_oracle_golden.py docstring):
+  smooth images max-abs <= 1e-3 and PSNR >= 75 dB; uniform white noise max-abs <= 2e-3, <= 0.2 % of the pixels beyond 1e-3,
+  PSNR >= 68 dB.  Returns (max, mean, PSNR) for reporting."""
+  ref = c['ref16'] if ref is None else ref
+  assert y.shape == ref.shape
+  d = np.abs(y - ref)
+  p = psnr(y, ref)
+  if is_white_noise(c):
+    assert d.max() <= 2e-3 and (d > 1e-3).mean() <= 2e-3 and p >= 68.0, (c['name'], what, d.max(), (d > 1e-3).mean(), p)
+  else:
+    assert d.max() <= 1e-3 and p >= 75.0, (c['name'], what, d.max(), p)
+  return float(d.max()), float(d.mean()), p

@@ -1,11 +1,15 @@
 """Parity tests proper (-m gpu): the CUDA path, called through the reference-shaped API and the C ABI,
 against the oracle and the golden vectors of the unmodified reference.
 
-Tolerances (DESIGN.md §numerics), all stated here:
-  * vs oracle mode 'f16io' (identical rounding points, fp32 accumulation in another order): max-abs <= 1e-3
-    (one fp16 ulp at 1.0 is 9.77e-4) — BASELINE's "1e-3 max-abs fp16".
-  * vs the reference's own fp32 CPU output (goldens): PSNR >= 60 dB (measured 71-75 dB), max-abs <= 1.5e-2
-    (the tail is the fp16 rounding of the WEIGHTS, which the reference's GPU path has too).
+Tolerances (DESIGN.md §3), all stated here:
+  * vs the reference's OWN fp16 output (goldens `<case>.ref16`: the unmodified reference in its GPU fp16 configuration,
+    executed on CPU) and vs the oracle in mode 'ref16' (same rounding points, restated in numpy/C) — helpers.assert_ref16_bar:
+      smooth images        max-abs <= 1e-3 (one fp16 ulp at 1.0 is 9.77e-4) and PSNR >= 75 dB — BASELINE's "1e-3 max-abs fp16";
+      uniform white noise  max-abs <= 2e-3 (two ulps), <= 0.2 % of the pixels beyond 1e-3, PSNR >= 68 dB.
+    The white-noise bar is not a loosening for the engine: it is how far two exact implementations of the SAME rounding
+    contract are apart when only the fp32 summation order inside conv2d differs (oracle vs reference, CPU only:
+    profiles/r02_parity_oracle_vs_reference.txt; the reference's cuDNN path vs its CPU path: test_reference_gpu_port_*).
+  * vs the reference's fp32 CPU output (goldens `.ref`): PSNR >= 60 dB (the north-star bar).
   * integer frame conversions, band sharding, determinism: bit-exact.
 """
 import ctypes
@@ -20,14 +24,17 @@ pytestmark = pytest.mark.gpu
 
 
 def _conv_ref(x, w, bias, r, epi, param, skip):
+  """fp32 convolution, then the epilogue with the reference's per-op fp16 roundings (csrc/conv_tc.cuh::epi_apply)"""
+  q = lambda t: t.half().float()
   xn = x.float().permute(0, 3, 1, 2)
   y = torch.nn.functional.conv2d(xn, w.float(), None if bias is None else bias.float(), padding=1)
   if epi == 1:
+    y = q(y)
     y = torch.where(y >= 0, y, param * y)
   elif epi == 2:
-    y = skip.float().permute(0, 3, 1, 2) + param * y
+    y = skip.float().permute(0, 3, 1, 2) + q(param * q(y))
   elif epi == 3:
-    y = torch.nn.functional.pixel_shuffle(y, r) if r > 1 else y
+    y = q(torch.nn.functional.pixel_shuffle(y, r) if r > 1 else y)
     y = torch.where(y >= 0, y, param * y)
   return y.permute(0, 2, 3, 1).contiguous()
 
@@ -72,7 +79,7 @@ def test_conv3x3_tcgen05_matches_fp32_reference_and_simt(engine, n, h, w, r, epi
   simt = _run_conv(engine, x, wt, bias, r, epi, 0.25, skip).float()
   engine.set_conv_path(simt=False)
   assert not torch.isnan(tc).any() and not torch.isnan(simt).any()
-  tol = 2.0 ** -10 * torch.clamp(ref.abs(), min=1.0) + 1e-4          # one fp16 ulp of the result + accumulation noise
+  tol = 2.0 ** -10 * torch.clamp(ref.abs(), min=1.0) + 2.5e-4        # one fp16 ulp of the result + a flipped intermediate rounding
   assert ((tc - ref).abs() <= tol).all()
   assert ((simt - ref).abs() <= tol).all()
   # same rounding points, different fp32 summation order: equal up to one fp16 ulp on a small fraction
@@ -85,11 +92,11 @@ def test_golden_cases_through_the_reference_api(engine, name):
   c = H.load_case(name)
   y = H.run_case_engine(c)                  # asserts the tile plan equals the reference's too
   assert y.shape == c['ref'].shape
-  orc = H.run_case_oracle(c, mode='f16io')
-  assert np.abs(y - orc).max() <= 1e-3
-  d = np.abs(y - c['ref'])
+  got = H.assert_ref16_bar(y, c, what='engine vs the reference fp16 golden')
+  orc = H.assert_ref16_bar(y, c, ref=H.run_case_oracle(c, mode='ref16'), what='engine vs oracle ref16')
+  print('PARITY %-16s vs reference fp16: max %.2e mean %.2e PSNR %.1f dB | vs oracle ref16: max %.2e PSNR %.1f dB | vs reference fp32: PSNR %.1f dB'
+        % (name, got[0], got[1], got[2], orc[0], orc[2], H.psnr(y, c['ref'])))
   assert H.psnr(y, c['ref']) >= 60.0
-  assert d.max() <= 1.5e-2 and np.quantile(d, .999) <= 4e-3
   if c['alpha'] is not None:
     assert np.array_equal(y[3], c['alpha'].astype(np.float16).astype(np.float32))
 
@@ -175,10 +182,9 @@ def test_bare_network_call_matches_oracle(engine):
   x = torch.rand(2, 1, 37, 53, generator=torch.Generator().manual_seed(2)).half()
   y = opt(x.cuda())
   assert tuple(y.shape) == (2, 1, 148, 212)
-  want = N.forward(sd, x.float().numpy(), mode='f16io')
+  want = N.forward(sd, x.float().numpy(), mode='ref16')
   d = np.abs(y.float().cpu().numpy() - want)
-  # white-noise input is the worst case for fp16 ulp flips propagating through 20 layers: two ulps at 1.0
-  assert d.max() <= 2e-3 and (d > 1e-3).mean() < 1e-3
+  assert d.max() <= 2e-3 and (d > 1e-3).mean() <= 2e-3          # the white-noise bar (module docstring)
 
 
 def test_frame_conversions_are_bit_exact(engine):
@@ -219,6 +225,7 @@ def test_strength_and_alpha(engine):
 
 
 def test_ensemble_is_the_average_of_the_dihedral_passes(engine):
+  """structure check; the values are checked against the reference by the goldens a2_ens3 / a2_ens7"""
   from moephoto_b200 import runSR, imageProcess as IP
   from moephoto_b200.config import config
   config.freeMemOverride = int(4e9)
@@ -298,7 +305,7 @@ def test_errors_are_status_codes_not_crashes(engine):
 def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
   """BASELINE configs[3] in miniature: two 16-bit frames (bgr48le as video.py pipes them) -> toTorch(16) ->
   DN lite15 -> SR a2 -> toOutput(16), frames batched as planes (bit-identical to per-frame calls
-  when cropsize is pinned), checked against the oracle with the engine's rounding points."""
+  when cropsize is pinned), checked against the oracle (mode 'ref16')."""
   from oracle import net as N, tiling as T
   from moephoto_b200 import runSR, runDN, imageProcess as IP
   from moephoto_b200.config import config
@@ -322,10 +329,11 @@ def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
     for i, f in enumerate(frames):
       xi = T.to_planar(f[:, :, ::-1], 16, np.float16).astype(np.float32)
       pd = T.make_plan((3, 40, 56), 4e9, .95 / 1253.4, 7, 1, 8, 32)
-      d = T.rgb_filter(lambda a: N.forward(sdn, a, mode='f16io'), xi, pd, 1.0, np.float16).astype(np.float32)
+      d = T.rgb_filter(lambda a: N.forward(sdn, a, mode='ref16'), xi, pd, 1.0, np.float16).astype(np.float32)
       ps = T.make_plan((3, 40, 56), 4e9, .9 / 2473., 5, 2, 8, 32)
-      s = T.do_crop(lambda a: N.forward(ssr, a, mode='f16io'), d, ps, np.float16)
-      assert np.abs(y[3 * i:3 * i + 3].float().cpu().numpy() - s.astype(np.float32)).max() <= 2e-3
+      s = T.do_crop(lambda a: N.forward(ssr, a, mode='ref16'), d, ps, np.float16)
+      dd = np.abs(y[3 * i:3 * i + 3].float().cpu().numpy() - s.astype(np.float32))
+      assert dd.max() <= 2e-3 and (dd > 1e-3).mean() <= 2e-3      # noisy 16-bit frames through two networks: the white-noise bar
       want = T.to_output(s.astype(np.float32), 16)[:, :, ::-1]
       assert np.abs(out[i].astype(np.int64) - (want.astype(np.int64) & 0xFFFF)).max() <= 140        # 2e-3 * 65536
   finally:
@@ -344,8 +352,7 @@ def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags
         y = H.run_case_engine(c)
     finally:
         engine.set_conv_path()
-    orc = H.run_case_oracle(c, mode='f16io')
-    assert np.abs(y - orc).max() <= 1e-3
+    H.assert_ref16_bar(y, c, what='variant vs the reference fp16 golden')
     assert H.psnr(y, c['ref']) >= 60.0
     assert np.abs(y - y_default).max() <= 1e-3
     if flags.get('static_sched'):
@@ -377,7 +384,7 @@ def test_fused_path_at_4k_tile_width(engine):
                                              ('lite2', 2, (3, 3, 5)), ('lite8', 8, (1, 9, 131))])
 def test_degenerate_and_ragged_shapes(engine, key, scale, shape):
     """smallest inputs the reference accepts (a single tile padded to 8 by reflect-then-zero padImage), widths just
-    over one 128-px strip, plane counts 1..4 — against the oracle with the engine's rounding points"""
+    over one 128-px strip, plane counts 1..4 — against the oracle (mode 'ref16')"""
     from oracle import net as N, tiling as T
     from moephoto_b200 import imageProcess as IP
     from moephoto_b200.config import config
@@ -389,11 +396,9 @@ def test_degenerate_and_ragged_shapes(engine, key, scale, shape):
         sd = H.load_weights(key)
         plan = T.make_plan(shape, int(4e9), opt.ramCoef, opt.padding, scale, 8, 0)
         assert plan.tiles == opt.plan.tiles and (plan.pad_h, plan.pad_w) == (opt.plan.pad_h, opt.plan.pad_w)
-        want = T.do_crop(lambda a: N.forward(sd, a, mode='f16io'), x.float().numpy(), plan, np.float16).astype(np.float32)
+        want = T.do_crop(lambda a: N.forward(sd, a, mode='ref16'), x.float().numpy(), plan, np.float16).astype(np.float32)
         d = np.abs(y.float().cpu().numpy() - want)
-        # white-noise input is the worst case for fp16 ulp flips (see test_bare_network_call): two ulps at 1.0, three
-        # through the three PixelShuffle stages of lite8; never more than 0.2 % of the pixels beyond one ulp
-        assert d.max() <= 3e-3 and (d > 1e-3).mean() < 2e-3
+        assert d.max() <= 2e-3 and (d > 1e-3).mean() <= 2e-3      # the white-noise bar (module docstring), every net
     finally:
         config.freeMemOverride = None
 
@@ -426,7 +431,7 @@ def test_full_size_4k_a4_bench_workload(engine):
         yc = opt(crop.unsqueeze(1))[:, 0]                               # bare network on the crop, zero padded at its border
         m = 16
         assert torch.equal(yc[:, 4 * m:4 * (s - m), 4 * m:4 * (s - m)], y[:, 4 * (cy + m):4 * (cy + s - m), 4 * (cx + m):4 * (cx + s - m)])
-        want = N.forward(H.load_weights('a4'), crop.float().cpu().numpy()[:, None], mode='f16io')[:, 0]
+        want = N.forward(H.load_weights('a4'), crop.float().cpu().numpy()[:, None], mode='ref16')[:, 0]
         assert np.abs(yc.float().cpu().numpy() - want).max() <= 1e-3
     finally:
         config.freeMemOverride = None
@@ -454,3 +459,54 @@ def test_frame_batched_video_route_equals_per_frame_calls(engine):
         assert all(np.array_equal(halves[i % 2][i], want[i]) for i in range(5))
     finally:
         config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
+
+
+@pytest.mark.parametrize('name', H.band_case_names())
+def test_large_goldens_every_seam_band_against_the_reference(engine, name):
+    """a4 on a 512x1024 frame cut into 3x6 tiles, and on a 96x3840 frame cut into the four column strips of the
+    reference's 4K plan (same column anchors as the bench workload): every seam band (full length) and interior windows of
+    the reference's fp16-configuration output, smooth-image bar"""
+    c = H.load_band_case(name)
+    y = H.run_case_engine(c)
+    assert tuple(y.shape[1:]) == (c['img'].shape[0] * c['scale'], c['img'].shape[1] * c['scale'])
+    worst, sq, npx = 0.0, 0.0, 0
+    for (y0, y1, x0, x1), want in c['windows']:
+        d = np.abs(y[:, y0:y1, x0:x1] - want)
+        worst = max(worst, float(d.max()))
+        sq += float((d.astype(np.float64) ** 2).sum())
+        npx += d.size
+    p = 10 * np.log10(1.0 / max(sq / npx, 1e-20))
+    print('PARITY %-16s %d tiles, %d windows (%.1f MPix) vs reference fp16: max %.2e PSNR %.1f dB' % (name, len(c['tiles']), len(c['windows']), npx / 1e6, worst, p))
+    assert worst <= 1e-3 and p >= 75.0
+
+
+def test_blend_ramp_equals_the_reference_sigmoid_on_cuda_in_half(engine):
+    """the reference evaluates the seam ramp on the GPU in half (imageProcess.py:109); the engine's host-side ramp
+    (imageProcess.blendRamp) must give the same fp16 values for every seam width the served models produce"""
+    from moephoto_b200 import imageProcess as IP
+    for pad_sc in (7, 10, 14, 20, 27, 40):                        # dn 7x1, a2 5x2, (dn chained) 7x2, a4 / lite4 5x4, a3 9x3, lite8 5x8
+        want = ((torch.arange(pad_sc, dtype=torch.half, device='cuda') / pad_sc - .5) * 9).sigmoid()
+        got = torch.from_numpy(IP.blendRamp(pad_sc)).half()
+        assert torch.equal(got, want.cpu()), pad_sc
+
+
+@pytest.mark.parametrize('name', ['a2_tiled', 'a4_single', 'a3_tiled', 'dn15_tiled', 'lite4_single', 'a4_rand', 'lite4_rand'])
+def test_reference_gpu_port_and_engine_are_equally_close_to_the_reference_goldens(engine, name):
+    """/root/reference does not exist on the GPU box, so the reference's GPU arithmetic is reproduced by the oracle's
+    PyTorch port run in half on CUDA (cuDNN conv2d, aten prelu / pixel_shuffle / add: op for op what the reference's
+    nn.Modules launch; oracle/net.py::forward_torch) under the oracle's doCrop.  Three-way comparison against the golden
+    the unmodified reference produced on CPU in the same fp16 configuration: the engine must meet the bar, and must not be
+    further from the golden than the cuDNN port is (+ half an ulp of slack on the maximum)."""
+    from oracle import net as N, tiling as T
+    c = H.load_case(name)
+    y = H.run_case_engine(c)
+    sd = H.load_weights(c['weights'])
+    x = H.case_input(c, np.float16).astype(np.float32)
+    net = lambda a: N.forward_torch(sd, a, dtype='float16', device='cuda')
+    plan = H.oracle_plan(c)
+    port = (T.do_crop(net, x, plan, np.float16) if c['kind'] == 'sr' else T.rgb_filter(net, x, plan, 1.0, np.float16)).astype(np.float32)
+    de, dp, dep = np.abs(y - c['ref16']), np.abs(port - c['ref16']), np.abs(y - port)
+    print('PARITY %-16s engine vs golden: max %.2e mean %.2e | cuDNN-half port vs golden: max %.2e mean %.2e | engine vs port: max %.2e mean %.2e'
+          % (name, de.max(), de.mean(), dp.max(), dp.mean(), dep.max(), dep.mean()))
+    H.assert_ref16_bar(y, c)
+    assert de.max() <= dp.max() + 5e-4 and de.mean() <= 2.0 * dp.mean() + 1e-5

@@ -159,3 +159,45 @@ def test_lite_network_forward_matches_reference(ref, upscale, ckpt):
   assert N.arch_of_state_dict(sd) == 'lite'
   got = N.forward(sd, x.numpy())
   assert got.shape == want.shape and np.abs(got - want).max() < 2e-5
+
+
+@pytest.mark.parametrize('ckpt,getopt,key', [('a4/model_new.pth', ('runSR', {'model': 'a', 'scale': 4}), 'SRa4'),
+                                             ('a3/model_new.pth', ('runSR', {'model': 'a', 'scale': 3}), 'SRa3'),
+                                             ('dn_lite15/model_new.pth', ('runDN', {'model': 'lite15'}), 'DNlite15'),
+                                             ('lite/model.pth', ('runSR', {'model': 'lite', 'scale': 2}), 'SRlite2')])
+def test_ref16_mode_matches_the_reference_run_in_half(ref, ckpt, getopt, key):
+  """mode='ref16' restates the rounding points of `model.half()` on half tensors (imageProcess.py:309-318 castModel):
+  the UNMODIFIED reference network, cast to half and run live on CPU, against the numpy/C restatement on white noise —
+  the worst case.  Identical rounding points, different fp32 summation order inside conv2d: <= 2 fp16 ulps at 1.0,
+  (almost) no pixel beyond one ulp, and far closer than the round-1 contract (one rounding per stored tensor)."""
+  x = torch.rand(2, 40, 56, generator=torch.Generator().manual_seed(11)).half()
+  with R.gpu_fp16_config():
+    getattr(ref[getopt[0]], 'getOpt')(dict(getopt[1]))
+    net = R.bare_net(key)
+    with torch.no_grad():
+      want = net(x.unsqueeze(1))[-1]
+    assert want.dtype == torch.half
+    want = want.float().numpy()
+  sd = N.to_numpy_state(R.state_dict(ckpt))
+  xn = x.float().numpy()[:, None]
+  got, old = N.forward(sd, xn, mode='ref16'), N.forward(sd, xn, mode='f16io')
+  d = np.abs(got - want)
+  assert d.max() <= 2e-3 and (d > 1e-3).mean() <= 2e-3
+  assert d.mean() < 0.8 * np.abs(old - want).mean()
+
+
+def test_ensemble_restatement_matches_reference(ref):
+  """T.ensemble (imageProcess.py:558-572 + runSR.py:26) against the reference's own sr() with ensemble = 1..7, fp32, on a
+  non-square tiled image (the transposed passes run on the plan of the transposed shape)"""
+  x = torch.rand(3, 44, 70, generator=torch.Generator().manual_seed(21))
+  sd = N.to_numpy_state(R.state_dict('a2/model_new.pth'))
+  ram = 4e9
+  ref['config'].calcFreeMem = lambda *a, **k: int(ram)
+  for k in (1, 4, 7):
+    want, tiles, opt = R.run_sr(x, 2, crop=48, ensemble=k)
+    coef = float(opt.ramCoef)
+    plan = T.make_plan((3, 44, 70), int(ram), coef, 5, 2, 8, 48)
+    plan_t = T.make_plan((3, 70, 44), int(ram), coef, 5, 2, 8, 48)
+    assert plan.tiles == [tuple(int(v) for v in t) for t in tiles]
+    got = T.ensemble(lambda a: N.forward(sd, a), x.numpy(), plan, plan_t, k)
+    assert got.shape == tuple(want.shape) and np.abs(got - want.numpy()).max() < 2e-5, k

@@ -105,9 +105,9 @@ def golden_suite(eng):
         ref = c['ref']
         d = np.abs(y - ref)
         psnr = 10 * np.log10(1.0 / max(np.mean(d ** 2), 1e-20))
-        orc = Hh.run_case_oracle(c, mode='f16io')
+        orc = Hh.run_case_oracle(c, mode='ref16')
         d2 = np.abs(y - orc)
-        say('[golden %s] %-16s vs ref fp32: max %.3e psnr %.1f dB | vs oracle f16io: max %.3e  frac>1e-3 %.2e' %
+        say('[golden %s] %-16s vs ref fp32: max %.3e psnr %.1f dB | vs oracle ref16: max %.3e  frac>1e-3 %.2e' %
             ('simt' if simt else 'tc  ', name, d.max(), psnr, d2.max(), (d2 > 1e-3).mean()))
       except Exception as ex:
         say('[golden %s] %-16s EXCEPTION %r' % ('simt' if simt else 'tc', name, ex))
