@@ -292,8 +292,8 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = q * 8 + e * 2;
-              const float f0 = epi_apply(__uint_as_float(v[j]), EPI_BIAS_PRELU, p.param, bb[e * 2], 0.f);
-              const float f1 = epi_apply(__uint_as_float(v[j + 1]), EPI_BIAS_PRELU, p.param, bb[e * 2 + 1], 0.f);
+              const float f0 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j]), p.param, bb[e * 2], 0.f, p.bias_fused);
+              const float f1 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j + 1]), p.param, bb[e * 2 + 1], 0.f, p.bias_fused);
               const __half2 hv = __floats2half2_rn(f0, f1);
               w[e] = *reinterpret_cast<const uint32_t*>(&hv);
             }
@@ -368,6 +368,7 @@ __device__ __forceinline__ void pair_trunk_decode(const ConvParams& p, int item,
   y1 = min(p.H, y0 + p.seg_rows);
 }
 
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
 {
@@ -510,13 +511,13 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
     const int half = (warp - 2) >> 2;
     const int L = lgrp * 32 + lane;
     const bool lead_warp = (warp == 2);
-    const bool has_skip = p.epi == EPI_SCALE_SKIP;
+    constexpr bool has_skip = EPI == EPI_SCALE_SKIP;
     uint8_t* my_row = stg_ptr + L * 128;
     const int sw = L & 7;
     const uint32_t tempty_leader = ptx::mapa(tempty, 0);
     float bias_r[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) bias_r[j] = p.epi == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
+    for (int j = 0; j < 32; ++j) bias_r[j] = EPI == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
     uint32_t acc = 0;
     // residual prefetch cursor: walks the same row sequence kSkipAhead rows ahead of the epilogue
     int c_item = -1, c_n = 0, c_sp = 0, c_y = 0, c_y1 = 0;
@@ -582,8 +583,8 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
               s0 = __low2float(hs);
               s1 = __high2float(hs);
             }
-            const float f0 = epi_apply(__uint_as_float(v[j]), p.epi, p.param, bias_r[j], s0);
-            const float f1 = epi_apply(__uint_as_float(v[j + 1]), p.epi, p.param, bias_r[j + 1], s1);
+            const float f0 = epi_apply<EPI>(__uint_as_float(v[j]), p.param, bias_r[j], s0, p.bias_fused);
+            const float f1 = epi_apply<EPI>(__uint_as_float(v[j + 1]), p.param, bias_r[j + 1], s1, p.bias_fused);
             const __half2 hv = __floats2half2_rn(f0, f1);
             w[e] = *reinterpret_cast<const uint32_t*>(&hv);
           }

@@ -6,12 +6,16 @@
 //     layout of a K-major UMMA A operand — and, instead of a TMA store, a SECOND tcgen05.mma stream
 //     (M = 256 over the pair, N = 16 = 9 taps padded, K = 64) multiplies it with the head filter:
 //     P_t(Y,X) = <w_head[t], act(Y,X,:)>, fp32 in TMEM;
-//   * four reader warps move P (9 floats per pixel) to a planar fp32 buffer: 36 B per pixel instead of 128 B,
-//     and the 2 x 12.8 GB intermediate tensors of an a4 tile are never written or read.  Each branch keeps its
-//     own P array: the reference's half model rounds each head to fp16 BEFORE adding them (models.py:38), so the
-//     two stencil sums must stay apart (round 1 added branch 2 onto branch 1's array — the same HBM traffic, as a
-//     read-modify-write inside this kernel);
-//   * head_stencil_kernel (below) sums the 3x3 stencil of P_u and of P_r, rounds each, adds, rounds, blends, stores.
+//   * four reader warps take P (9 floats per output pixel) out of TMEM and do the HORIZONTAL third of the head's 3x3
+//     stencil on the spot: H_dy(Y,X) = (P[dy,0](Y,X-1) + P[dy,1](Y,X)) + P[dy,2](Y,X+1).  A lane owns the output pixels
+//     2x and 2x+1 of one row, its neighbours' terms arrive by warp shuffle (across the four warps through a 96-byte
+//     shared-memory exchange); only the terms that cross the 256-output-pixel strip of the CTA are unavailable — they
+//     are exported to a small edge array (6 floats per strip and row) and added by the stencil kernel.  What leaves
+//     the kernel is 3 floats per output pixel (12 B) instead of 9 (36 B, round 1) or the 128 B of the unfused path; the
+//     2 x 12.8 GB intermediate tensors of an a4 tile are never written or read.  Each branch keeps its own array: the
+//     reference's half model rounds each head to fp16 BEFORE adding them (models.py:38);
+//   * head_stencil_kernel (below) finishes vertically: S = (H_0(Y-1) + H_1(Y)) + H_2(Y+1) per branch, rounds each, adds,
+//     rounds, blends, stores: 2 x 12 + 2 B per output pixel.
 // Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader) / weight handshake (peer), 2..9 epilogue,
 // 10 head-MMA issuer (leader), 11..14 P readers.  TMEM: 3 accumulator stages x 128 columns + 2 P stages x 32.
 #pragma once
@@ -23,7 +27,8 @@ namespace moe {
 struct PairHeadParams {
   ConvParams c;            // the convolution (r = 2, EPI_BIAS_PRELU); c.out is unused
   const uint8_t* head_img; // [16 rows][128 B] swizzled fp16: rows 0..8 = the 9 taps of THIS branch's head filter
-  float* pbuf;             // [N][9][2H][2W] fp32, this branch's array
+  float* hbuf;             // [N][3][2H][2W] fp32: this branch's H_dy planes
+  float* ebuf;             // [N][2H][2 * strips][6] fp32: per CTA strip and output row, {first pixel's P[dy,2], last pixel's P[dy,0]}
 };
 
 constexpr int kPairHeadThreads = 15 * 32;
@@ -34,7 +39,7 @@ struct PairHeadCfg {
   static constexpr int kPStages = 2;
   static constexpr uint32_t kPCol0 = kAccStages * 128;     // 384
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kChunkImgBytes + 2 * kStageBytes + 1024 + 1024;
+  static constexpr uint32_t kSmemBytes = 1024 + kSlots * kSlotBytes + kChunkImgBytes + 2 * kStageBytes + 1024 + 1024 + 256;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairHeadThreads, 1)
@@ -57,6 +62,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   const uint32_t wbar = pempty + 8 * PS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
   const uint32_t sq_items = bars + 256, sq_bars = bars + 320;       // item queue (kSchedQ ints + kSchedQ barriers), ends at +448
   const uint32_t bias_sm = bars + 512;                              // 128 floats, 16-byte aligned
+  float* xch_ptr = reinterpret_cast<float*>(smem + (bars + 1024 - base));   // P readers' exchange: [2 rows in flight][4 warps][6] floats
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
   uint8_t* stg_ptr = smem + (stg - base);
   float* bias_ptr = reinterpret_cast<float*>(smem + (bias_sm - base));
@@ -212,8 +218,8 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = q * 8 + e * 2;
-              const float f0 = epi_apply(__uint_as_float(v[j]), EPI_BIAS_PRELU, p.param, bb[e * 2], 0.f);
-              const float f1 = epi_apply(__uint_as_float(v[j + 1]), EPI_BIAS_PRELU, p.param, bb[e * 2 + 1], 0.f);
+              const float f0 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j]), p.param, bb[e * 2], 0.f, p.bias_fused);
+              const float f1 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j + 1]), p.param, bb[e * 2 + 1], 0.f, p.bias_fused);
               const __half2 hv = __floats2half2_rn(f0, f1);
               w[e] = *reinterpret_cast<const uint32_t*>(&hv);
             }
@@ -269,18 +275,21 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
       ptx::mbar_wait(dbar, 0);
     }
   } else {
-    // ------------------------------------------------------------ P readers (warps 11..14): TMEM -> planar fp32 in HBM
-    const int lgrp = warp & 3;
+    // ------------------------------------------------------------ P readers (warps 11..14): TMEM -> horizontal stencil third -> HBM
+    const int lgrp = warp & 3;                       // TMEM lane quadrant of this warp = pixels 32*lgrp .. +31 of the strip
     const int L = lgrp * 32 + lane;
     const uint32_t pempty_leader = ptx::mapa(pempty, 0);
     const int Ho = p.H * 2, Wo = p.W * 2;
     const size_t plane = static_cast<size_t>(Ho) * Wo;
+    const int estrips = 2 * p.strips;                // CTA strips per row (p.strips counts strip PAIRS)
     uint32_t acc = 0;
     uint32_t ord = 0;
     for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
       int g, n, sp, y0, y1;
       pair_decode_item(p, item, g, n, sp, y0, y1);
-      const int x = (sp * 2 + static_cast<int>(rank)) * kStripW + L;
+      const int strip = sp * 2 + static_cast<int>(rank);
+      const int x = strip * kStripW + L;
+      const bool valid = x < p.W;                     // pixels right of the tile are zero padding for the head convolution
       for (int y = y0; y < y1; ++y, ++acc) {
         const uint32_t ps = acc % PS;
         ptx::mbar_wait(pfull + 8 * ps, (acc / PS) & 1);
@@ -292,12 +301,37 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(pempty_leader + 8 * ps);
-        if (x < p.W) {
-          // chunk c of this pair's group g is sub-pixel (i, j) = (g, c): output pixel (2y + g, 2x + c)
-          float* dst = hp.pbuf + static_cast<size_t>(n) * 9 * plane + static_cast<size_t>(2 * y + g_fixed) * Wo + 2 * x;
+        // chunk c of this pair's group g is sub-pixel (i, j) = (g, c): v0 = output pixel (2y + g, 2x), v1 = (2y + g, 2x + 1)
+        float c0[9], c1[9];
 #pragma unroll
-          for (int t = 0; t < 9; ++t)
-            *reinterpret_cast<float2*>(dst + t * plane) = make_float2(__uint_as_float(v0[t]), __uint_as_float(v1[t]));
+        for (int t = 0; t < 9; ++t) { c0[t] = valid ? __uint_as_float(v0[t]) : 0.f; c1[t] = valid ? __uint_as_float(v1[t]) : 0.f; }
+        float left[3], right[3];                      // P[dy,0] of output pixel 2x - 1, P[dy,2] of output pixel 2x + 2
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          left[dy] = __shfl_up_sync(0xffffffffu, c1[dy * 3 + 0], 1);
+          right[dy] = __shfl_down_sync(0xffffffffu, c0[dy * 3 + 2], 1);
+        }
+        float* xr = xch_ptr + (acc & 1) * 24;
+        if (lane == 31) { xr[lgrp * 6 + 0] = c1[0]; xr[lgrp * 6 + 1] = c1[3]; xr[lgrp * 6 + 2] = c1[6]; }
+        if (lane == 0) { xr[lgrp * 6 + 3] = c0[2]; xr[lgrp * 6 + 4] = c0[5]; xr[lgrp * 6 + 5] = c0[8]; }
+        ptx::named_bar_sync(3, 128);                  // the four reader warps; two exchange buffers, so one barrier per row suffices
+        float* erow = hp.ebuf + ((static_cast<size_t>(n) * Ho + (2 * y + g_fixed)) * estrips + strip) * 6;
+        if (lane == 0) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) left[dy] = lgrp > 0 ? xr[(lgrp - 1) * 6 + dy] : 0.f;
+          if (lgrp == 0) { erow[0] = c0[2]; erow[1] = c0[5]; erow[2] = c0[8]; }      // the strip to the left needs these
+        }
+        if (lane == 31) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) right[dy] = lgrp < 3 ? xr[(lgrp + 1) * 6 + 3 + dy] : 0.f;
+          if (lgrp == 3) { erow[3] = c1[0]; erow[4] = c1[3]; erow[5] = c1[6]; }      // the strip to the right needs these
+        }
+        if (valid) {
+          float* dst = hp.hbuf + static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(2 * y + g_fixed) * Wo + 2 * x;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+            *reinterpret_cast<float2*>(dst + dy * plane) =
+                make_float2((left[dy] + c0[dy * 3 + 1]) + c1[dy * 3 + 2], (c0[dy * 3 + 0] + c1[dy * 3 + 1]) + right[dy]);
         }
       }
     }
@@ -313,84 +347,71 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   }
 }
 
-// out(Y,X) = round16( round16(S_u) + round16(S_r) ), S_b = sum_{dy,dx} P_b[dy*3+dx](Y+dy-1, X+dx-1), zero outside the
-// computed rectangle, then the seam blend and the canvas store of head_blend_kernel / head_tc_kernel.
-// A thread owns 4 consecutive pixels of a row: per tap plane ONE aligned 16-byte load (two 8-byte loads when the row
-// pitch is not a multiple of 4 floats); the dx = -1 / +1 taps take their fourth value from the neighbouring lane
-// (shuffle; the warp's edge lanes load it).  A block therefore reads 2 KB of contiguous floats per plane row instead of
-// the 1 KB of misaligned 4-byte loads of the one-pixel-per-thread version (3.6 TB/s, profiles/r01_bench_n1_final.json).
+// out(Y,X) = round16( round16(S_u) + round16(S_r) ), S_b = (H^b_0(Y-1,X) + H^b_1(Y,X)) + H^b_2(Y+1,X), zero outside the computed
+// rectangle; at the two pixels of a row that touch the border of a 256-pixel CTA strip the horizontal term the convolution
+// kernel could not reach comes from the edge array.  Then the seam blend and the canvas store of head_blend_kernel /
+// head_tc_kernel.  A thread owns 4 consecutive pixels of a row: six aligned 16-byte loads (two 8-byte loads each when the
+// row pitch is not a multiple of 4 floats), every H value is read exactly once.
 struct HeadStencilParams {
   HeadParams g;            // geometry, seam and canvas (u/r/wu/wr unused)
-  const float* pu;         // [N][9][H][W]: P of branch `u`
-  const float* pr;         // same for branch `convt_R1`
+  const float* hu;         // [N][3][H][W]: H_dy planes of branch `u`
+  const float* hr;         // same for branch `convt_R1`
+  const float* eu;         // [N][H][estrips][6] edge terms of branch `u`
+  const float* er;
+  int estrips;
 };
 
 constexpr int kStencilThreads = 128;
 constexpr int kStencilPx = 4;
+constexpr int kStencilStripOut = 2 * kStripW;     // output pixels per CTA strip of the convolution kernel
 
 __global__ void __launch_bounds__(kStencilThreads) head_stencil_kernel(const HeadStencilParams p)
 {
   const HeadParams& g = p.g;
-  const int lane = threadIdx.x & 31;
   const int x = (blockIdx.x * kStencilThreads + threadIdx.x) * kStencilPx;
   const int n = blockIdx.z;
+  if (x >= g.W) return;
   const size_t plane = static_cast<size_t>(g.H) * g.W;
-  const float* bp[2] = {p.pu + static_cast<size_t>(n) * 9 * plane, p.pr + static_cast<size_t>(n) * 9 * plane};
-  const bool vec4 = (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(bp[0]) | reinterpret_cast<uintptr_t>(bp[1])) & 15) == 0 &&
+  const float* hb[2] = {p.hu + static_cast<size_t>(n) * 3 * plane, p.hr + static_cast<size_t>(n) * 3 * plane};
+  const float* eb[2] = {p.eu + static_cast<size_t>(n) * g.H * p.estrips * 6, p.er + static_cast<size_t>(n) * g.H * p.estrips * 6};
+  const bool vec4 = (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(hb[0]) | reinterpret_cast<uintptr_t>(hb[1])) & 15) == 0 &&
                     (plane & 3) == 0;                            // rows of every plane 16-byte aligned
-  const int nvalid = min(kStencilPx, g.W - x);       // <= 0: this thread is right of the rectangle (it still shuffles)
-  // the whole warp must reach the shuffles: no early return
+  const int nvalid = min(kStencilPx, g.W - x);
+  const int strip = x / kStencilStripOut;
+  const bool fix_left = x % kStencilStripOut == 0 && strip > 0;                              // pixel 0 of this thread
+  const bool fix_right = x % kStencilStripOut == kStencilStripOut - kStencilPx && x + kStencilPx < g.W;   // pixel 3
   for (int y = blockIdx.y; y < g.H; y += gridDim.y) {            // gridDim.y is capped at 65535 rows
     const int cy = g.oy + y;
-    const bool row_kept = cy >= g.keep_y0 && cy < g.keep_y1;     // uniform over the block
-    if (!row_kept) continue;
+    if (cy < g.keep_y0 || cy >= g.keep_y1) continue;
     float head[2][kStencilPx];                                   // the two heads' stencil sums, each rounded to fp16
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      const float* bu = bp[b];
-      float acc[3][kStencilPx];                                  // [dy][pixel]: (t(dx=0) + t(dx=1)) + t(dx=2), as head_blend_kernel
+      float h[3][kStencilPx];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
         const int yy = y + dy - 1;
-        const bool in_y = yy >= 0 && yy < g.H;                   // uniform over the block
-        float s[3][kStencilPx];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          float v[kStencilPx] = {0.f, 0.f, 0.f, 0.f};
-          const float* row = bu + static_cast<size_t>(dy * 3 + dx) * plane + static_cast<size_t>(in_y ? yy : 0) * g.W;
-          if (in_y && nvalid > 0) {
-            if (nvalid == kStencilPx && vec4) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(row + x));
-              v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-            } else if (nvalid == kStencilPx && ((reinterpret_cast<uintptr_t>(row + x) & 7) == 0)) {
-              const float2 q0 = __ldg(reinterpret_cast<const float2*>(row + x));
-              const float2 q1 = __ldg(reinterpret_cast<const float2*>(row + x + 2));
-              v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
-            } else {
+        for (int i = 0; i < kStencilPx; ++i) h[dy][i] = 0.f;
+        if (yy < 0 || yy >= g.H) continue;
+        const float* row = hb[b] + static_cast<size_t>(dy) * plane + static_cast<size_t>(yy) * g.W + x;
+        if (nvalid == kStencilPx && vec4) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(row));
+          h[dy][0] = q.x; h[dy][1] = q.y; h[dy][2] = q.z; h[dy][3] = q.w;
+        } else if (nvalid == kStencilPx && ((reinterpret_cast<uintptr_t>(row) & 7) == 0)) {
+          const float2 q0 = __ldg(reinterpret_cast<const float2*>(row));
+          const float2 q1 = __ldg(reinterpret_cast<const float2*>(row + 2));
+          h[dy][0] = q0.x; h[dy][1] = q0.y; h[dy][2] = q1.x; h[dy][3] = q1.y;
+        } else {
 #pragma unroll
-              for (int i = 0; i < kStencilPx; ++i) if (i < nvalid) v[i] = __ldg(row + x + i);
-            }
-          }
-          if (dx == 1) {
-#pragma unroll
-            for (int i = 0; i < kStencilPx; ++i) s[1][i] = v[i];
-          } else if (dx == 0) {                                  // pixel i needs column x + i - 1
-            float left = __shfl_up_sync(0xffffffffu, v[3], 1);
-            if (lane == 0) left = (in_y && nvalid > 0 && x > 0) ? __ldg(row + x - 1) : 0.f;
-            s[0][0] = left; s[0][1] = v[0]; s[0][2] = v[1]; s[0][3] = v[2];
-          } else {                                               // pixel i needs column x + i + 1
-            float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-            if (lane == 31) right = (in_y && x + kStencilPx < g.W) ? __ldg(row + x + kStencilPx) : 0.f;
-            s[2][0] = v[1]; s[2][1] = v[2]; s[2][2] = v[3]; s[2][3] = right;
-          }
+          for (int i = 0; i < kStencilPx; ++i) if (i < nvalid) h[dy][i] = __ldg(row + i);
         }
-#pragma unroll
-        for (int i = 0; i < kStencilPx; ++i) acc[dy][i] = (s[0][i] + s[1][i]) + s[2][i];
+        const float* e = eb[b] + (static_cast<size_t>(yy) * p.estrips) * 6;
+        if (fix_left) h[dy][0] += __ldg(e + (strip - 1) * 6 + 3 + dy);        // P[dy,0] of the last pixel of the strip to the left
+        if (fix_right) h[dy][3] += __ldg(e + (strip + 1) * 6 + dy);           // P[dy,2] of the first pixel of the strip to the right
       }
 #pragma unroll
-      for (int i = 0; i < kStencilPx; ++i) head[b][i] = h_round((acc[0][i] + acc[1][i]) + acc[2][i]);
+      for (int i = 0; i < kStencilPx; ++i) head[b][i] = h_round((h[0][i] + h[1][i]) + h[2][i]);
     }
-    if (nvalid <= 0) continue;
     __half* dst = g.canvas + n * g.plane_stride + static_cast<int64_t>(cy) * g.row_stride + (g.ox + x);
     float out[kStencilPx];
     bool keep[kStencilPx];

@@ -42,6 +42,7 @@ struct ConvParams {
   float param;            // PReLU slope or residual scale
   int strips, nseg, seg_rows, items;
   int center_only;        // 1: a 1x1 convolution packed as a centre-tap 3x3 filter (MoeNet_lite2): issue only tap (1,1)
+  int bias_fused;         // EPI_BIAS_PRELU: 0 = q(q(conv) + bias) (the reference on the GPU), 1 = q(conv + bias) (the half model on the CPU)
   // pair kernels only (conv_pair.cuh, "item scheduler"):
   int dynamic;            // 1: pairs draw their next item from the global counters, 0: round-robin by pair index
   int* sched;             // device int[kSchedInts]: per-chunk-group item counters + the count of finished pairs; all 0 between launches
@@ -91,13 +92,34 @@ __device__ __forceinline__ float h_round(float v) { return __half2float(__float2
 // multiply (models.py:73) and the residual add (models.py:60) are separate ops.  Returns the value BEFORE the final
 // rounding of the store (the caller packs with __floats2half2_rn).  Products / sums of two fp16 values are exact
 // in fp32, so rounding them to fp16 afterwards is the single rounding the reference's fp32-opmath kernels do.
-__device__ __forceinline__ float epi_apply(float v, int epi, float param, float bias, float skip) {
-  if (epi == EPI_PRELU) { v = h_round(v); return v >= 0.f ? v : param * v; }
-  if (epi == EPI_SCALE_SKIP) return h_round(h_round(v) * param) + skip;
-  if (epi == EPI_BIAS_PRELU) { v = h_round(v + bias); return v >= 0.f ? v : param * v; }
+// A convolution WITH a bias is two ops on the GPU: aten runs cudnn_convolution without the bias, then output.add_(bias)
+// — q(q(conv) + bias), measured on B200 (profiles/r02_cudnn_rounding_probe.log).  bias_fused = 1 selects q(conv + bias),
+// what the CPU execution of the half model does (oneDNN adds the bias inside the convolution; the committed `.ref16`
+// goldens were produced that way): moe_engine_set_conv_path bit 5.
+template <int EPI>
+__device__ __forceinline__ float epi_apply(float v, float param, float bias, float skip, int bias_fused) {
+  if (EPI == EPI_PRELU) { v = h_round(v); return v >= 0.f ? v : param * v; }
+  if (EPI == EPI_SCALE_SKIP) return h_round(h_round(v) * param) + skip;
+  if (EPI == EPI_BIAS_PRELU) {
+    const float t = bias_fused ? v : h_round(v);       // a select, not a branch: the epilogue is unrolled 32 values deep
+    v = h_round(t + bias);
+    return v >= 0.f ? v : param * v;
+  }
   return v;
 }
+// run-time epilogue selector for the cross-check kernel (kernels_simt.cuh); the tensor-core kernels are compiled per epilogue:
+// with `epi` a run-time value the compiler branched per accumulator value, 525 branches in the trunk kernel, and the
+// epilogue warps fell behind the MMA stream (trunk convolutions 26 -> 35 ms per 4K frame, profiles/r02_bench_epilogue_branches.txt)
+__device__ __forceinline__ float epi_apply_rt(float v, int epi, float param, float bias, float skip, int bias_fused) {
+  switch (epi) {
+    case EPI_PRELU: return epi_apply<EPI_PRELU>(v, param, bias, skip, bias_fused);
+    case EPI_SCALE_SKIP: return epi_apply<EPI_SCALE_SKIP>(v, param, bias, skip, bias_fused);
+    case EPI_BIAS_PRELU: return epi_apply<EPI_BIAS_PRELU>(v, param, bias, skip, bias_fused);
+    default: return v;
+  }
+}
 
+template <int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
 {
@@ -219,12 +241,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     const int half = (warp - 2) >> 2;                // which 32 of the 64 channels
     const int L = lgrp * 32 + lane;                  // pixel within the strip == staging row
     const bool lead_warp = (warp == 2);               // its elected lane issues the TMA stores / residual loads
-    const bool has_skip = p.epi == EPI_SCALE_SKIP;
+    constexpr bool has_skip = EPI == EPI_SCALE_SKIP;
     uint8_t* my_row = stg_ptr + L * 128;
     const int sw = L & 7;
     float bias_r[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) bias_r[j] = p.epi == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
+    for (int j = 0; j < 32; ++j) bias_r[j] = EPI == EPI_BIAS_PRELU ? __ldg(p.bias + chunk * 64 + half * 32 + j) : 0.f;
 
     uint32_t acc = 0;                                // output-row counter over ALL items
     if (has_skip && lead_warp && blockIdx.x < p.items) { // residual tile of the very first row
@@ -278,8 +300,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
               s0 = __low2float(hs);
               s1 = __high2float(hs);
             }
-            const float f0 = epi_apply(__uint_as_float(v[j]), p.epi, p.param, bias_r[j], s0);
-            const float f1 = epi_apply(__uint_as_float(v[j + 1]), p.epi, p.param, bias_r[j + 1], s1);
+            const float f0 = epi_apply<EPI>(__uint_as_float(v[j]), p.param, bias_r[j], s0, p.bias_fused);
+            const float f1 = epi_apply<EPI>(__uint_as_float(v[j + 1]), p.param, bias_r[j + 1], s1, p.bias_fused);
             const __half2 hv = __floats2half2_rn(f0, f1);
             w[e] = *reinterpret_cast<const uint32_t*>(&hv);
           }

@@ -65,6 +65,7 @@ struct MoeEngine {
   int no_pair = 0;         // 1 = keep every conv on the single-CTA kernel (A/B switch)
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
   int no_fuse = 0;         // 1 = last upsample conv and heads stay separate kernels (conv3x3_pair_kernel + head_tc_kernel)
+  int bias_fused = 0;      // 1 = biased convolutions round once, q(conv + bias): the half model executed on the CPU (goldens); 0 = the GPU's two ops
   int static_sched = 0;    // 1 = pair kernels deal their items round-robin instead of drawing them (conv_pair.cuh, item scheduler)
   int* d_sched = nullptr;  // the item scheduler's counters (kSchedInts ints, zero between launches)
   unsigned long long* dbg = nullptr;   // moe_engine_debug_buffer: per-pair {start ns, end ns, SM id, items} of the LAST pair-kernel launch
@@ -169,7 +170,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   ConvParams p{};
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
   p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param; p.center_only = center_only;
-  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg;
+  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg; p.bias_fused = e->bias_fused;
   // algorithmic FLOPs: 2 * taps * Cin * Cout per input pixel (padded channels are not counted)
   Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
   if (e->simt) {
@@ -239,12 +240,16 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   }
   if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d H=%d W=%d r=%d", (int)cr, N, H, W, r);
   if (pair_trunk) {
+    // one instantiation per epilogue: the epilogue arithmetic is straight-line code for the 32 accumulator values a thread owns
+    typedef void (*TrunkFn)(const ConvMaps, const ConvParams);
+    static const TrunkFn trunk_fn[4] = {conv3x3_pair_trunk_kernel<EPI_PLAIN>, conv3x3_pair_trunk_kernel<EPI_PRELU>,
+                                        conv3x3_pair_trunk_kernel<EPI_SCALE_SKIP>, conv3x3_pair_trunk_kernel<EPI_BIAS_PRELU>};
     if (!e->pair_trunk_attr_set) {
-      MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairTrunkCfg::kSmemBytes));
+      for (int i = 0; i < 4; ++i) MOE_CUDA(cudaFuncSetAttribute(trunk_fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, PairTrunkCfg::kSmemBytes));
       e->pair_trunk_attr_set = true;
     }
     const int npairs = static_cast<int>(std::min<int64_t>(e->sm_count / 2 / ncg1 * ncg1, p.items));   // p.items is a multiple of r*r
-    conv3x3_pair_trunk_kernel<<<2 * npairs, kConvThreads, PairTrunkCfg::kSmemBytes, st>>>(maps, p);
+    trunk_fn[epi]<<<2 * npairs, kConvThreads, PairTrunkCfg::kSmemBytes, st>>>(maps, p);
     return check_launch(e, "conv3x3_pair_trunk_kernel");
   }
   if (pair_path) {
@@ -256,24 +261,27 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
     conv3x3_pair_kernel<<<2 * npairs, kConvThreads, PairCfg::kSmemBytes, st>>>(maps, p);
     return check_launch(e, "conv3x3_pair_kernel");
   }
+  typedef void (*ConvFn)(const ConvMaps, const ConvParams);
+  static const ConvFn conv_fn[4] = {conv3x3_tc_kernel<EPI_PLAIN>, conv3x3_tc_kernel<EPI_PRELU>, conv3x3_tc_kernel<EPI_SCALE_SKIP>,
+                                    conv3x3_tc_kernel<EPI_BIAS_PRELU>};
   if (!e->smem_attr_set) {
-    MOE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg::kSmemBytes));
+    for (int i = 0; i < 4; ++i) MOE_CUDA(cudaFuncSetAttribute(conv_fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg::kSmemBytes));
     e->smem_attr_set = true;
   }
-  conv3x3_tc_kernel<<<grid, kConvThreads, ConvCfg::kSmemBytes, st>>>(maps, p);
+  conv_fn[epi]<<<grid, kConvThreads, ConvCfg::kSmemBytes, st>>>(maps, p);
   return check_launch(e, "conv3x3_tc_kernel");
 }
 
 // ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
 int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, int N, int H, int W,
-                     float slope, const uint8_t* head_img, float* pbuf, int center_only = 0)
+                     float slope, const uint8_t* head_img, float* hbuf, float* ebuf, int center_only = 0)
 {
   PairHeadParams hp{};
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
   p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
-  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg;
-  hp.head_img = head_img; hp.pbuf = pbuf;
+  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg; p.bias_fused = e->bias_fused;
+  hp.head_img = head_img; hp.hbuf = hbuf; hp.ebuf = ebuf;
   Timed timed(e, st, 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
   const int npairs_max = (e->sm_count / 2) & ~1;
   const int strips1 = (W + kStripW - 1) / kStripW;
@@ -497,6 +505,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   e->no_pair_trunk = (simt >> 2) & 1;
   e->no_fuse = (simt >> 3) & 1;
   e->static_sched = (simt >> 4) & 1;
+  e->bias_fused = (simt >> 5) & 1;
   return MOE_OK;
 }
 
@@ -694,7 +703,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
         if ((rc = launch_conv(e, st, bufM, bufC, nullptr, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
         frm_partial_kernel<<<dim3(kFrmBlocks, N), 256, 0, st>>>(bufC, partial, px);
         if ((rc = check_launch(e, "frm_partial_kernel")) != MOE_OK) return rc;
-        frm_gate_kernel<<<N, 64, 0, st>>>(partial, m->frm[b], gate, 1.0f / static_cast<float>(px));
+        frm_gate_kernel<<<N, 64, 0, st>>>(partial, m->frm[b], gate, 1.0f / static_cast<float>(px), e->bias_fused);
         if ((rc = check_launch(e, "frm_gate_kernel")) != MOE_OK) return rc;
         frm_apply_kernel<<<grid_for(px * N * 8, 256, e->sm_count), 256, 0, st>>>(bufC, bufT, gate, px, N);
         if ((rc = check_launch(e, "frm_apply_kernel")) != MOE_OK) return rc;
@@ -711,13 +720,20 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     // the two upsample stacks: branch 0 on `out`, branch 1 on the trunk           models.py:29-33,125-154; MoeNet_lite2.py:47-50
     const __half* head_in[2] = {bufA, bufT};
     const bool fuse = !e->simt && !e->no_pair && !e->no_fuse && m->n_up >= 1 && m->r == 2 && e->sm_count >= 4;
-    float* pbuf[2] = {nullptr, nullptr};
+    float* hbuf[2] = {nullptr, nullptr};
+    float* ebuf[2] = {nullptr, nullptr};
+    int estrips = 0;
     if (m->n_up >= 1 && m->r == 2) {
       __half* stage_buf[2] = {reinterpret_cast<__half*>(up0), reinterpret_cast<__half*>(up0 + 4 * unit)};   // S1 (4 units), S2 (16 units)
       uint8_t* fin = up0 + stage_units(m) * unit;
       size_t fin_units = 1;
       for (int i = 0; i < m->n_up; ++i) fin_units *= 4;
-      for (int b = 0; b < 2; ++b) pbuf[b] = reinterpret_cast<float*>(fin + b * fin_units * unit);   // fused: one P array per branch (36 of the 128 B per pixel)
+      // fused: per branch the three H_dy planes (12 of the 128 B per output pixel) and, behind them, the strip-edge terms
+      estrips = 2 * ((((W << (m->n_up - 1)) + kStripW - 1) / kStripW + 1) / 2);
+      for (int b = 0; b < 2; ++b) {
+        hbuf[b] = reinterpret_cast<float*>(fin + b * fin_units * unit);
+        ebuf[b] = hbuf[b] + static_cast<size_t>(N) * 3 * (static_cast<size_t>(H) * sc) * (static_cast<size_t>(W) * sc);
+      }
       for (int b = 0; b < 2; ++b) {
         const __half* src = b ? bufT : bufA;
         for (int s2 = 0; s2 < m->n_up; ++s2) {
@@ -727,7 +743,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
           const float* wb = m->up_bias[4 * b + s2];
           const float slope = m->scalars[14 + 4 * b + s2];
           if (last && fuse) {
-            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, pbuf[b], one_by_one)) != MOE_OK) return rc;
+            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, hbuf[b], ebuf[b], one_by_one)) != MOE_OK) return rc;
           } else {
             __half* dst = last ? reinterpret_cast<__half*>(fin + b * fin_units * unit) : stage_buf[s2];
             if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
@@ -758,10 +774,10 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
     if (fuse) {
       HeadStencilParams sp{};
-      sp.g = hp; sp.pu = pbuf[0]; sp.pr = pbuf[1];
+      sp.g = hp; sp.hu = hbuf[0]; sp.hr = hbuf[1]; sp.eu = ebuf[0]; sp.er = ebuf[1]; sp.estrips = estrips;
       dim3 sgrid((hp.W + kStencilThreads * kStencilPx - 1) / (kStencilThreads * kStencilPx), std::min(hp.H, 65535), N);
       if (sgrid.z > 65535u) return fail(MOE_ERR_INVALID, "too many planes for the stencil kernel grid");
-      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (72 + 2));   // bytes: two 9-float reads, one fp16 write
+      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (24 + 2));   // bytes: two 3-float reads, one fp16 write
       head_stencil_kernel<<<sgrid, kStencilThreads, 0, st>>>(sp);
     } else if (e->simt) {
       dim3 hgrid((hp.W + 127) / 128, hp.H, N);

