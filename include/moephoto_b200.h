@@ -103,7 +103,8 @@ int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t 
  * bit 4: 1 = the CTA-pair kernels deal their work items round-robin instead of drawing them from a counter;
  * bit 5: numerics of a convolution WITH a bias (models.py:29-30): 0 (default) = q(q(conv) + bias), what the reference's GPU
  *        path computes (aten: cudnn_convolution, then add_ of the bias — two ops, two fp16 roundings), 1 = q(conv + bias), what
- *        the same half model computes on the CPU (oneDNN adds the bias inside the convolution; tests/golden `.ref16`) */
+ *        the same half model computes on the CPU (oneDNN adds the bias inside the convolution; tests/golden `.ref16`);
+ * bit 6: 1 = run every residual block (ARSB) as two convolution launches instead of the fused arsb_pair_kernel */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
 /* Diagnostics: `dev` = device buffer of >= 4 * 8 bytes per SM pair (or NULL to switch off).  Every CTA-pair convolution
  * launch then leaves {start ns, end ns, SM id, items processed} per pair in it (the last launch wins). */

@@ -18,6 +18,7 @@
 #include "conv_tc.cuh"
 #include "conv_pair.cuh"
 #include "conv_pair_head.cuh"
+#include "conv_arsb.cuh"
 #include "kernels_simt.cuh"
 #include "head_tc.cuh"
 
@@ -65,6 +66,8 @@ struct MoeEngine {
   int no_pair = 0;         // 1 = keep every conv on the single-CTA kernel (A/B switch)
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
   int no_fuse = 0;         // 1 = last upsample conv and heads stay separate kernels (conv3x3_pair_kernel + head_tc_kernel)
+  int no_arsb = 0;         // 1 = every residual block as two launches of the trunk kernel instead of arsb_pair_kernel (A/B switch)
+  bool arsb_attr_set = false;
   int bias_fused = 0;      // 1 = biased convolutions round once, q(conv + bias): the half model executed on the CPU (goldens); 0 = the GPU's two ops
   int static_sched = 0;    // 1 = pair kernels deal their items round-robin instead of drawing them (conv_pair.cuh, item scheduler)
   int* d_sched = nullptr;  // the item scheduler's counters (kSchedInts ints, zero between launches)
@@ -270,6 +273,46 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   }
   conv_fn[epi]<<<grid, kConvThreads, ConvCfg::kSmemBytes, st>>>(maps, p);
   return check_launch(e, "conv3x3_tc_kernel");
+}
+
+// ---- one residual block t' = t + scale * conv_2(PReLU(conv_1(t))) as one kernel (conv_arsb.cuh) ----
+int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, const uint8_t* w1_img, const uint8_t* w2_img,
+                int N, int H, int W, float slope, float scale)
+{
+  ArsbParams ap{};
+  ConvParams& p = ap.c;
+  p.w_img = w1_img; p.in = in; p.out = out; p.N = N; p.H = H; p.W = W; p.r = 1; p.epi = EPI_PRELU; p.param = slope;
+  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg;
+  ap.w2_img = w2_img; ap.scale = scale;
+  Timed timed(e, st, 1, 2 * 2.0 * 9 * e->cur_feat * static_cast<double>(e->cur_feat) * N * H * W);   // both convolutions
+  const int npairs_max = e->sm_count / 2;
+  const int strips1 = (W + kArsbStripW - 1) / kArsbStripW;
+  p.strips = (strips1 + 1) / 2;                                // strip PAIRS of 2 x 126 px
+  const int64_t base_items = static_cast<int64_t>(N) * p.strips;
+  choose_segments(base_items, npairs_max, H, 16, &p.seg_rows, &p.nseg);
+  const int64_t items = base_items * p.nseg;
+  if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
+  p.items = static_cast<int>(items);
+  ArsbMaps maps;
+  memset(&maps, 0, sizeof maps);
+  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  const cuuint64_t strides[3] = {128, dims[1] * 128, dims[1] * dims[2] * 128};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint32_t box_in[4] = {64, kRowPx, 1, 1}, box_out[4] = {64, kArsbStripW, 1, 1};
+  CUresult cr = e->encode(&maps.in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box_in, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr == CUDA_SUCCESS)
+    cr = e->encode(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out, dims, strides, box_out, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the residual block", (int)cr);
+  if (!e->arsb_attr_set) {
+    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfg::kSmemBytes));
+    e->arsb_attr_set = true;
+  }
+  const int npairs = static_cast<int>(std::min<int64_t>(npairs_max, p.items));
+  arsb_pair_kernel<<<2 * npairs, kConvThreads, ArsbCfg::kSmemBytes, st>>>(maps, ap);
+  return check_launch(e, "arsb_pair_kernel");
 }
 
 // ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
@@ -506,6 +549,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   e->no_fuse = (simt >> 3) & 1;
   e->static_sched = (simt >> 4) & 1;
   e->bias_fused = (simt >> 5) & 1;
+  e->no_arsb = (simt >> 6) & 1;
   return MOE_OK;
 }
 
@@ -710,10 +754,18 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
       }
     } else {
       // six ARSBs: t += scale * conv_2(PReLU(conv_1(t)))                        models.py:76-80
+      const bool fused_arsb = !e->simt && !e->no_pair && !e->no_pair_trunk && !e->no_arsb && e->sm_count >= 2;
+      __half* cur = bufT;
+      __half* other = bufM;                                     // the fused kernel cannot update t in place (strips read each other's halo columns)
       for (int b = 0; b < 6; ++b) {
         const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
-        if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
-        if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
+        if (fused_arsb) {
+          if ((rc = launch_arsb(e, st, cur, other, m->trunk_img[l1], m->trunk_img[l2], N, H, W, m->scalars[1 + l1], m->scalars[1 + l2])) != MOE_OK) return rc;
+          std::swap(cur, other);                                 // six blocks: the result ends up in bufT again
+        } else {
+          if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+          if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
+        }
       }
     }
 

@@ -62,11 +62,11 @@ class Engine:
     d['conv3x3'] = tuple(a + b for a, b in zip(d['conv_trunk'], d['conv_up']))      # every 3x3 tensor-core convolution
     return d
 
-  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False, static_sched=False, bias_fused=False):
+  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False, static_sched=False, bias_fused=False, no_arsb=False):
     """A/B switches of the engine.  bias_fused: biased convolutions round once, q(conv + bias), as when the reference's half
     model is executed on the CPU (how the `.ref16` goldens were made); default = the GPU's q(q(conv) + bias)."""
     _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(no_pair)) << 1) | (int(bool(no_pair_trunk)) << 2) |
-                                                 (int(bool(no_fuse)) << 3) | (int(bool(static_sched)) << 4) | (int(bool(bias_fused)) << 5)))
+                                                 (int(bool(no_fuse)) << 3) | (int(bool(static_sched)) << 4) | (int(bool(bias_fused)) << 5) | (int(bool(no_arsb)) << 6)))
 
   def debug_buffer(self, tensor):
     """tensor: int64 CUDA tensor of >= 4 values per SM pair, or None; see moe_engine_debug_buffer"""

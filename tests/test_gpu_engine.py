@@ -363,7 +363,7 @@ def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
     config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
 
 
-@pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True), dict(static_sched=True)])
+@pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True), dict(static_sched=True), dict(no_arsb=True)])
 @pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'lite2_tiled', 'lite8_single'])
 def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags):
     """the A/B switches keep the single-CTA conv kernel, the unfused CTA-pair kernel and head_tc_kernel alive;
@@ -378,8 +378,10 @@ def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags
     H.assert_ref16_bar(y, c, ref=H.run_case_oracle(c, mode='ref16'), what='variant vs oracle ref16')
     assert H.psnr(y, c['ref']) >= 60.0
     assert np.abs(y - y_default).max() <= 1e-3
-    if flags.get('static_sched'):
-        assert np.array_equal(y, y_default)          # who computes an item never changes its result
+    if flags.get('static_sched') or flags.get('no_arsb'):
+        # who computes an item never changes its result; and the fused residual block has the rounding points AND the MMA
+        # accumulation order of its two-launch form
+        assert np.array_equal(y, y_default)
 
 
 def test_fused_path_at_4k_tile_width(engine):
@@ -539,3 +541,30 @@ def test_reference_gpu_port_and_engine_are_equally_close_to_the_reference_golden
         # two exact implementations are further apart than on the conv-only nets; the engine must not be further from the
         # CPU golden than the reference's own GPU arithmetic is
         assert de.max() <= dp.max() + 1e-3 and de.mean() <= 1.5 * dp.mean() + 1e-5
+
+
+@pytest.mark.parametrize('key,scale,shape,crop', [('a4', 4, (3, 150, 300), 0), ('a2', 2, (2, 97, 127), 0), ('a2', 2, (1, 40, 126), 0), ('a2', 2, (3, 33, 253), 0),
+                                                  ('dn_lite15', 1, (3, 260, 380), 0), ('a3', 3, (1, 19, 500), 0), ('a4', 4, (3, 300, 200), 96)])
+def test_fused_residual_block_is_bit_identical_to_its_two_launch_form(engine, key, scale, shape, crop):
+    """arsb_pair_kernel (conv_1 + PReLU + conv_2 + x scale + skip with the intermediate rows in shared memory, 126-px strips)
+    against two launches of conv3x3_pair_trunk_kernel (128-px strips): same rounding points, same accumulation order ->
+    the same bits, on widths around the strip boundaries (126, 127, 252, 253), several row segments, 1-3 planes, tiled plans"""
+    from moephoto_b200 import runDN, imageProcess as IP
+    from moephoto_b200.config import config
+    try:
+        if key.startswith('dn'):
+            config.freeMemOverride = int(178 * 2 ** 30 * .9)
+            opt = runDN.getOpt({'model': 'lite15'}, weights=H.load_weights(key))
+        else:
+            opt = _sr_opt(key, scale, crop)
+        x = torch.rand(shape, generator=torch.Generator().manual_seed(sum(shape))).half().cuda()
+        y = IP.doCrop(opt, x)
+        engine.set_conv_path(no_arsb=True)
+        try:
+            y2 = IP.doCrop(opt, x)
+        finally:
+            engine.set_conv_path()
+        assert torch.isfinite(y).all()
+        assert torch.equal(y, y2)
+    finally:
+        config.freeMemOverride = None
