@@ -10,7 +10,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libmoephoto_b200.so')
+# MOE_B200_LIB: load another build of the same ABI (A/B timing of two builds inside one GPU session, tools/)
+LIB_PATH = os.environ.get('MOE_B200_LIB') or os.path.join(HERE, 'lib', 'libmoephoto_b200.so')
 SOURCES = [os.path.join(HERE, 'csrc', 'engine.cu')]
 HEADERS = [os.path.join(HERE, 'csrc', n) for n in sorted(os.listdir(os.path.join(HERE, 'csrc'))) if n.endswith(('.cuh', '.h'))] + \
           [os.path.join(HERE, '..', 'include', 'moephoto_b200.h')]
