@@ -6,13 +6,19 @@
            convolutions of Net4x, seam-blended and stitched on the device.
   N GPUs : the SAME frame, canvas rows sharded over the ranks (moephoto_b200/parallel.py): broadcast of
            the LR frame, per-rank row band + 16-px recompute halo, NCCL gather into rank 0 -> "strong".
-  value  : frame resident in HBM (fp16 planar) -> stitched fp16 canvas resident in HBM on rank 0.
+  value  : frame resident in HBM (fp16 planar) -> stitched fp16 canvas resident in HBM on rank 0; the engine's per-launch
+           profiler is OFF in this timed region (the per-kernel breakdown comes from a second pass).
   e2e    : uint8 HWC frame in pinned HOST memory -> uint8 HWC result in HOST memory, through the C-ABI
            (moe_enhance_host at N=1; at N>1 parallel.sharded_enhance_host: every rank converts and copies its own
            band into a shared page-locked host frame), copies timed.
+  roofline : the dominant kernel (conv3x3_pair_head_kernel) and, under `kernels`, every kernel class with its own algorithmic
+           work (halo rows, padded channels and scrap columns are NOT counted), CUDA-event time, fraction of
+           the measured peak and ncu DRAM bytes per launch (profiles/traffic.json, one capture session of this build).
+  configs  : the other named configurations of BASELINE.json (C1 256x256 a2, C2 1080p a2, C4 dn_lite15 -> a2 on 16 x 1080p,
+           C5 a3 on 64 x 4K, frames sharded over the ranks) measured in the same run, after the headline.
   --impl reference : the reference's CPU path (PyTorch conv2d on the host cores, fp32) restated by the
            oracle port (oracle/net.py forward_torch + oracle/tiling.py), all host threads, on a
-           bounded sample of the same workload (a 256x256 crop per step).
+           bounded sample of the same workload (a 512x512 crop per step).
 
 Prints ONE JSON line on rank 0.  Synthetic data, real a4 weights when tests/golden/weights_a4.npz is
 present (it is committed), else seeded random weights of the same architecture.
@@ -35,7 +41,8 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
 METRIC = 'output MPix/s, 4x SR (a4) on 3840x2160 RGB'
 H_IN, W_IN, SCALE = 2160, 3840, 4
 FLOP_PER_LR_PIXEL_PLANE = 3945600
-CPU_SAMPLE = int(os.environ.get('MOE_BENCH_CPU_SAMPLE', '256'))   # the CPU legs run a CPU_SAMPLE^2 crop per step
+CONV_FLOP_PER_LR_PIXEL_PLANE = 3907584     # its 3x3 convolutions 64 -> 64 / 256 (conv_input and the two heads excluded)
+CPU_SAMPLE = int(os.environ.get('MOE_BENCH_CPU_SAMPLE', '512'))   # the CPU legs run a CPU_SAMPLE^2 crop per step
 
 
 def a4_weights():
@@ -188,6 +195,34 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+# what each kernel class of the engine profiler is, for the roofline report: (kernel, bound, unit of the achieved figure)
+KERNELS = {
+  'conv_up_head': ('conv3x3_pair_head_kernel (last upsample conv 64->256 + PixelShuffle + PReLU fused with the heads\' dot products)', 'tensor'),
+  'conv_up': ('conv3x3_pair_kernel (first upsample conv 64->256 + PixelShuffle + PReLU)', 'tensor'),
+  'arsb': ('arsb_pair_kernel (one residual block: conv_1 + PReLU + conv_2 + x scale + skip)', 'tensor'),
+  'conv_trunk': ('conv3x3_pair_trunk_kernel (conv_input2, 64->64)', 'tensor'),
+  'conv_input': ('conv_first_kernel (1->64 + PReLU)', 'hbm'),
+  'head': ('head_stencil_kernel (vertical third of both head stencils, branch sum, seam blend, canvas store)', 'hbm'),
+}
+
+
+def kernel_rooflines(prof, steps, step_ms, pk, traffic, work_scale=1.0):
+  """per kernel class: time share, achieved algorithmic rate, fraction of the measured peak, ncu DRAM bytes per launch"""
+  out = {}
+  for cls, (name, bound) in KERNELS.items():
+    ms, work, n = prof[cls]
+    if n == 0 or ms <= 0:
+      continue
+    rate = work * work_scale / (ms * 1e-3)
+    peak = pk['tflops'] if bound == 'tensor' else pk['hbm']
+    achieved = rate / 1e12 if bound == 'tensor' else rate / 1e9
+    t = (traffic or {}).get(cls)
+    out[cls] = {'kernel': name, 'bound': bound, 'ms_per_step': ms / steps, 'share_of_step': ms / steps / step_ms, 'launches_per_step': n / steps,
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s' if bound == 'tensor' else 'GB/s', 'frac': achieved / peak,
+                'algorithmic_work_per_launch': work * work_scale / n, 'traffic': t}
+  return out
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -195,6 +230,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='native', choices=['native', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-extras', action='store_true', help='skip the other BASELINE configs, the parity figures and the eager-GPU baseline')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -240,11 +276,12 @@ def main():
   host_in = torch.from_numpy(frame_u8).pin_memory()
   host_out = torch.empty((H_IN * SCALE, W_IN * SCALE, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
   x = IP.toTorch(8)(frame_u8) if rank == 0 else torch.empty((3, H_IN, W_IN), dtype=torch.half, device=dev)
+  sharder = PAR.BandSharder(opt, (3, H_IN, W_IN), dev) if world > 1 else None
 
   def step():
     if world == 1:
       return runSR.sr(opt)(x)
-    return PAR.sharded_doCrop(opt, x)
+    return sharder.run(x)
 
   def sync():
     torch.cuda.synchronize()
@@ -273,15 +310,19 @@ def main():
   l0 = eng.launches()
   if sampler:
     sampler.mark()
-  eng.profile(True)
-  total_ms, y = timed(step, args.steps)
-  eng.profile(False)
-  prof = eng.profile_read()
+  total_ms, y = timed(step, args.steps)                   # THE timed region: profiler off
   clocks = sampler.stop() if sampler else None
   launches = eng.launches() - l0
   ms_step = total_ms / args.steps
   out_mpix = H_IN * SCALE * W_IN * SCALE / 1e6
   value = out_mpix / (ms_step / 1e3)
+
+  # ---- second pass, same steps, per-launch CUDA events on: the per-kernel breakdown (not part of `value`)
+  prof_steps = min(args.steps, 3)
+  eng.profile(True)
+  prof_total_ms, y = timed(step, prof_steps)
+  eng.profile(False)
+  prof = eng.profile_read()
 
   # ---- e2e: host uint8 frame -> host uint8 result, copies inside the timed region
   def e2e_step():
@@ -289,7 +330,7 @@ def main():
       _lib.check(eng.lib.moe_enhance_host(opt.modelCached.handle, ctypes.c_void_p(host_in.data_ptr()), 8, ctypes.byref(plan.c),
                                           ctypes.c_void_p(host_out.data_ptr()), 8, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
       return None
-    PAR.sharded_enhance_host(opt, host_in.numpy() if rank == 0 else None, shared_out, 8, 8)
+    sharder.run_host(host_in.numpy() if rank == 0 else None, shared_out, 8, 8)
     return None
 
   del y
@@ -306,10 +347,15 @@ def main():
     e2e_step()
   e2e_ms, _ = timed(e2e_step, args.steps)
   e2e_val = out_mpix / (e2e_ms / args.steps / 1e3)
-
   if shared_out is not None:
     dist.barrier()
     shared_out.close(unlink=(rank == 0))
+
+  # ---- the other named configurations (every rank takes part: frames are sharded over the ranks)
+  extras = None
+  if not args.no_extras:
+    extras = other_configs(rank, world, dev, sync)
+
   if rank != 0:
     if world > 1:
       dist.barrier()
@@ -317,12 +363,19 @@ def main():
     return
 
   pk = peaks()
-  conv_ms, conv_flops, conv_n = prof['conv3x3']
-  achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
   traffic = None
   tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
   if os.path.exists(tpath):
-    traffic = json.load(open(tpath)).get('conv3x3_tc_kernel_dram_bytes_per_launch')
+    traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+  # algorithmic work never counts halo rows: rank 0's band is in_h / world LR rows (its kernels computed up to 32 more)
+  lo, hi = PAR.band_rows(H_IN, 1, world, 0)
+  conv_ms, conv_flops, conv_n = prof['conv3x3']
+  alg_conv_flops = CONV_FLOP_PER_LR_PIXEL_PLANE * 3.0 * (hi - lo) * W_IN * prof_steps
+  work_scale = alg_conv_flops / conv_flops if conv_flops > 0 else 1.0          # 1.0 at N = 1 (no halo), < 1 on a band
+  prof_step_ms = prof_total_ms / prof_steps
+  kernels = kernel_rooflines(prof, prof_steps, prof_step_ms, pk, traffic if world == 1 else None, work_scale)
+  dom = kernels.get('conv_up_head', {})
+  achieved_all = alg_conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
   line = {
     'metric': METRIC, 'value': value, 'unit': 'MPix/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
     'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f16 storage / f32 accumulate',
@@ -330,23 +383,26 @@ def main():
     'config': {'workload': 'a4 (models.Net4x) 4x SR, one 3840x2160 RGB frame -> 15360x8640 (BASELINE configs[2])', 'weights': wsrc,
                'tile_plan': '%d reference tiles %s, pad 5, seam %d px' % (len(plan.tiles), [(t[1] - t[0], t[3] - t[2]) for t in plan.tiles][:4], plan.pad_sc),
                'parallelism': 'rows of the canvas sharded over %d GPU(s), 16-px recompute halo' % world,
-               'l2': 'per-layer activations are 0.8-51 GB per tile, far larger than the 126 MB L2; no flush needed'},
+               'l2': 'per-layer activations are 0.8-51 GB per tile, far larger than the 126 MB L2; no flush needed',
+               'numerics': 'the rounding points of the reference\'s GPU fp16 path (every aten op rounds; DESIGN.md §3)'},
     'clocks': clocks,
     'e2e': {'value': e2e_val, 'unit': 'MPix/s', 'ms_per_step': e2e_ms / args.steps, 'h2d_bytes_per_step': H_IN * W_IN * 3,
             'd2h_bytes_per_step': H_IN * SCALE * W_IN * SCALE * 3, 'path': 'moe_enhance_host (C ABI, pinned host uint8 in/out)' if world == 1 else
             'toTorch on rank 0 -> NCCL broadcast -> per-rank row band -> moe_to_output + D2H of each band into a shared page-locked host frame'},
     'gpu_launches': launches,
-    'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_pair_trunk_kernel + conv3x3_pair_kernel + conv3x3_pair_head_kernel (all %d 3x3-convolution launches of rank 0 in the timed region)' % conv_n,
-                 'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'peak_source': pk['src'],
-                 'traffic': traffic, 'avg_launch_ms': conv_ms / max(1, conv_n),
-                 'algorithmic_flops_per_launch': conv_flops / max(1, conv_n),
-                 'share_of_step': conv_ms / total_ms,
-                 'other_kernels': {k: {'ms_per_step': v[0] / args.steps, 'GBps': (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0), 'launches': v[2]}
-                                   for k, v in prof.items() if k in ('conv_input', 'head')},
-                 'conv_breakdown': {k: {'ms_per_step': v[0] / args.steps, 'TFLOPs': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), 'launches': v[2]}
-                                    for k, v in prof.items() if k in ('conv_trunk', 'conv_up')}},
+    'roofline': {'bound': 'tensor', 'kernel': dom.get('kernel'), 'achieved': dom.get('achieved'), 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                 'frac': dom.get('frac'), 'traffic': dom.get('traffic'), 'peak_source': pk['src'],
+                 'avg_launch_ms': dom.get('ms_per_step', 0) / max(1, dom.get('launches_per_step', 1)),
+                 'algorithmic_flops_per_launch': dom.get('algorithmic_work_per_launch'), 'share_of_step': dom.get('share_of_step'),
+                 'measured_in': 'a second pass of %d steps with the engine profiler on (%.2f ms per step; the timed region runs with it off)' % (prof_steps, prof_step_ms),
+                 'all_conv3x3': {'achieved': achieved_all, 'frac': achieved_all / pk['tflops'], 'ms_per_step': conv_ms / prof_steps,
+                                 'share_of_step': conv_ms / prof_total_ms, 'launches_per_step': conv_n / prof_steps,
+                                 'note': 'algorithmic FLOPs of the kept rows only (no halo recompute, no padded channels)'},
+                 'kernels': kernels},
     'whole_step_tflops': FLOP_PER_LR_PIXEL_PLANE * 3.0 * H_IN * W_IN / (ms_step * 1e-3) / 1e12,
   }
+  if extras:
+    line.update(extras)
   if world == 1 and not args.no_cpu_baseline:
     import torch as _t
     threads = host_threads()
@@ -356,11 +412,111 @@ def main():
     ts = [cpu_port_step(sd, crop, threads) for _ in range(3)]
     sec = min(ts)
     line['cpu_baseline'] = {'value': (CPU_SAMPLE * SCALE) ** 2 / 1e6 / sec, 'unit': 'MPix/s', 'cores': threads, 'kind': 'port',
-                            'sample': 'a4 on a %dx%d crop (1 warm-up, best of 3), oracle port with PyTorch CPU conv2d, fp32' % (CPU_SAMPLE, CPU_SAMPLE)}
+                            'sample': 'a4 on a %dx%d crop (1 warm-up, best of 3; a full 4K frame is %.0fx this, extrapolated by pixel count), oracle port '
+                                      'with PyTorch CPU conv2d, fp32' % (CPU_SAMPLE, CPU_SAMPLE, H_IN * W_IN / CPU_SAMPLE ** 2)}
   emit(line)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
+
+
+def other_configs(rank, world, dev, sync):
+  """BASELINE.json's other configurations, measured after the headline on the same GPUs (device-timed where the data is resident,
+  wall-clock over host-to-host frame streams; max over ranks).  Every rank calls this; rank 0 returns the report.
+    C1 256x256 a2 single tile            C2 1920x1080 -> 3840x2160 a2
+    C4 dn_lite15 -> a2 on 16 x 1080p     C5 a3 on 64 x 4K frames (frames dealt round-robin to the ranks, video.FrameBatcher)
+  plus, on rank 0 at N = 1: engine-vs-reference parity on a golden and the reference's GPU arithmetic (PyTorch eager, cuDNN
+  half) timed on the same device."""
+  import torch
+  import torch.distributed as dist
+  import helpers as H
+  from moephoto_b200 import runSR, runDN, imageProcess as IP, video
+  from moephoto_b200.config import config
+
+  def dev_timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+      fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+  def allmax(v):
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+  rep = {}
+  o2 = runSR.getOpt({'model': 'a', 'scale': 2}, weights=H.load_weights('a2'))
+  if rank == 0:
+    x = IP.toTorch(8)(synthetic_frame(256, 256, 1))
+    ms = dev_timed(lambda: runSR.sr(o2)(x), 10)
+    rep['C1'] = {'what': 'a2 on one 256x256 RGB tile -> 512x512, 1 GPU, device-resident', 'ms': ms, 'MPix/s': 0.262144 / ms * 1e3}
+    x = IP.toTorch(8)(synthetic_frame(1080, 1920, 2))
+    ms = dev_timed(lambda: runSR.sr(o2)(x), 5)
+    rep['C2'] = {'what': 'a2 1920x1080 -> 3840x2160 (%d reference tile), 1 GPU, device-resident' % len(o2.plan.tiles), 'ms': ms,
+                 'MPix/s': 8.2944 / ms * 1e3, 'frac_of_conv_flop_roofline': None}
+  # C4 / C5: host frames in, host frames out, frames sharded over the ranks
+  odn = runDN.getOpt({'model': 'lite15'}, weights=H.load_weights('dn_lite15'))
+  o3 = runSR.getOpt({'model': 'a', 'scale': 3}, weights=H.load_weights('a3'))
+  for key, opts, (h, w), n_frames, batch, out_mpix, what in (
+      ('C4', [odn, o2], (1080, 1920), 16, 8, 8.2944, 'dn_lite15 -> a2 chained on 16 x 1080p frames'),
+      ('C5', [o3], (2160, 3840), 64, 2, 74.6496, 'a3 3x SR on 64 x 3840x2160 frames (video path)')):
+    base = [synthetic_frame(h, w, 10 + i) for i in range(2)]
+    frames = [base[i % 2] for i in range(n_frames)]                        # frame CONTENT repeats, every frame is processed
+    mine = len([i for i in range(n_frames) if i % world == rank])
+    fb = video.FrameBatcher(opts, h, w, bit_depth=8, swap_rb=False, batch=min(batch, max(1, mine)))
+    for _ in fb.process(frames[:2 * world * fb.batch], rank, world, copy=False):   # warm-up: plans, workspaces, pinned staging
+      pass
+    sync()
+    t0 = time.perf_counter()
+    done = sum(1 for _ in fb.process(frames, rank, world, copy=False))
+    torch.cuda.synchronize()
+    sec = allmax(time.perf_counter() - t0)
+    assert done == mine
+    if rank == 0:
+      rep[key] = {'what': what + ', host uint8 frames in / out, frames dealt round-robin to %d GPU(s), %d frame(s) per engine call' % (world, fb.batch),
+                  'seconds': sec, 'frames_per_s': n_frames / sec, 'frames_per_s_per_gpu': n_frames / sec / world, 'MPix/s': n_frames * out_mpix / sec}
+    del fb
+    sync()
+  if rank != 0:
+    return None
+  out = {'configs': rep}
+  if world == 1:
+    # parity in the same run: the a4 golden through the public API against the reference's own fp16 output and the oracle
+    c = H.load_case('a4_single')
+    yg = H.run_case_engine(c)
+    yc = H.run_case_engine(c, cpu_bias=True)
+    orc = H.run_case_oracle(c, mode='ref16')
+    d1, d2 = np.abs(yc - c['ref16']), np.abs(yg - orc)
+    out['parity'] = {'case': 'a4_single golden (tests/golden/cases.npz, the UNMODIFIED reference in its GPU fp16 configuration, executed on CPU)',
+                     'engine_cpu_bias_mode_vs_reference_fp16': {'max_abs': float(d1.max()), 'psnr_db': H.psnr(yc, c['ref16'])},
+                     'engine_default_vs_oracle_ref16': {'max_abs': float(d2.max()), 'psnr_db': H.psnr(yg, orc)},
+                     'engine_default_vs_reference_fp32_psnr_db': H.psnr(yg, c['ref'])}
+    # the reference's GPU arithmetic on this device: PyTorch eager, cuDNN half, op for op what the reference's nn.Modules
+    # launch (oracle port; /root/reference does not exist on the GPU box), one reference tile of the 4K frame
+    try:
+      from oracle import net as ONet
+      sd, _ = a4_weights()
+      xt = torch.rand(3, 1, H_IN, 968, device=dev).half()
+      ONet.forward_torch(sd, xt[:, :, :64], dtype='float16', device='cuda')
+      torch.cuda.synchronize()
+      t0 = time.perf_counter()
+      ONet.forward_torch(sd, xt, dtype='float16', device='cuda')
+      torch.cuda.synchronize()
+      sec = time.perf_counter() - t0
+      out['gpu_eager_baseline'] = {'what': 'PyTorch eager fp16 (cuDNN) port of Net4x.forward on one 3 x 2160 x 968 reference tile incl. the copy of the '
+                                           'result to the host that the port ends with; a frame is 4 such tiles + stitching', 'seconds_per_tile': sec,
+                                   'MPix/s': 3 * 0 + (H_IN * SCALE * 968 * SCALE) / 1e6 / sec, 'kind': 'port'}
+    except Exception as ex:                                             # never let a baseline leg take the bench line down
+      out['gpu_eager_baseline'] = {'unavailable': repr(ex)[:200]}
+    finally:
+      torch.cuda.empty_cache()
+  return out
 
 
 if __name__ == '__main__':

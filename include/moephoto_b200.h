@@ -25,9 +25,12 @@
  * MoeStatus and never aborts the process; moe_last_error() gives the message for the calling thread's
  * last failure.  All device pointers are on the engine's device.  `stream` is a cudaStream_t passed as
  * void* (NULL = legacy default stream); work is enqueued on it and the call does not synchronise.
- * An engine and the models loaded into it are driven by one host thread at a time (MoePhoto's worker is a single
- * thread, worker.py:76-94) and by ONE stream at a time: its convolution launches share the work-item counters of the
- * engine and its workspace, so two of them must not run concurrently; different engines are independent.
+ * Concurrency: calls on one engine may come from several host threads and several streams.  Every convolution launch draws
+ * its work items from its own counter block, MoeNet_lite2's reduction scratch lives in the workspace the CALLER passes, so two
+ * moe_run_plan calls may overlap on two streams provided they are given two workspaces (and two canvases);
+ * moe_enhance_host* uses engine-owned staging buffers and serialises itself on a mutex.  The A/B switches
+ * (moe_engine_set_conv_path), the profiler and the debug buffer are engine-wide settings: change them only while no call is in
+ * flight.
  * There is NO CPU fallback: without a usable sm_100 device every compute entry point fails with
  * MOE_ERR_NO_DEVICE.
  */
@@ -90,12 +93,17 @@ int moe_engine_create(int device_id, MoeEngine** out);
 void moe_engine_destroy(MoeEngine* e);
 /* number of this library's kernels launched since the engine was created (bench.py "gpu_launches") */
 int64_t moe_engine_launch_count(const MoeEngine* e);
-/* Per-launch device timing for roofline reports: while enabled, every kernel launch is bracketed by
- * a CUDA event pair on its stream.  _read waits for them, returns per class (0 conv_input, 1 conv3x3 with
- * r = 1, 2 heads+blend, 3 upsample conv3x3 with PixelShuffle) the summed milliseconds, the summed algorithmic work (FLOPs for classes 1 and 3,
- * bytes otherwise) and the launch count, and resets the counters. */
+/* Per-launch device timing for roofline reports: while enabled, every kernel launch is bracketed by a CUDA event pair on its
+ * stream (two extra driver calls per launch: keep it OFF for throughput measurements).  _read waits for them and returns per
+ * kernel class the summed milliseconds, the summed ALGORITHMIC work (FLOPs for the convolution classes — padded channels,
+ * halo columns and scrap outputs are not counted — bytes otherwise) and the launch count, and resets the counters.  Classes:
+ *   0 conv_first_kernel (bytes)                      4 arsb_pair_kernel: one residual block, two convolutions (FLOPs)
+ *   1 3x3 conv 64->64 as its own launch (FLOPs)      5 conv3x3_pair_head_kernel: last upsample conv + head dot products (FLOPs)
+ *   2 head / stencil / blend / store (bytes)         6 MoeNet_lite2 FRM reduction + gate + apply (bytes)
+ *   3 upsample conv as its own launch (FLOPs)        7 reserved */
+#define MOE_PROFILE_CLASSES 8
 int moe_engine_profile(MoeEngine* e, int enable);
-int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t launches[4]);
+int moe_engine_profile_read(MoeEngine* e, double ms[MOE_PROFILE_CLASSES], double work[MOE_PROFILE_CLASSES], int64_t launches[MOE_PROFILE_CLASSES]);
 /* bit 0: 0 = tcgen05 tensor-core kernels (default), 1 = plain SIMT kernels (debug cross-check);
  * bit 1: 1 = keep every convolution on the single-CTA kernel instead of CTA pairs (A/B switch);
  * bit 2: 1 = only the 64->64 trunk convolutions stay on the single-CTA kernel;
@@ -156,6 +164,19 @@ int moe_to_output(MoeEngine* e, const void* src, int bits, int h, int w, int c, 
  * Uses the engine's internal device buffers (grown on demand). */
 int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePlan* plan,
                      void* host_out, int bits_out, void* stream);
+/* The same for frames of `channels` = 1 (grey), 3 or 4 (RGBA) interleaved samples.  As in the reference, an SR model upscales
+ * the alpha plane like a colour plane (one more element of the plane batch, runSR.py:39-40), a DN model (scale 1) filters the
+ * colour planes and passes alpha through untouched (_RGBFilter, imageProcess.py:370-377). */
+int moe_enhance_host_c(MoeModel* m, const void* host_in, int bits_in, int channels, const MoePlan* plan,
+                       void* host_out, int bits_out, void* stream);
+
+/* One row band of the result, for a frame sharded over several GPUs (moephoto_b200/parallel.py): `in` is the planar fp16 frame in
+ * DEVICE memory (it may be peer-mapped memory of another GPU: conv_first_kernel reads it in place), canvas rows [row_lo,row_hi)
+ * are computed into an engine-owned band buffer, converted and copied into rows [row_lo,row_hi) of `host_out` (the whole
+ * out_h x out_w x planes frame, e.g. a page-locked /dev/shm mapping every rank writes its own band of).  As in moe_enhance_host
+ * the conversion and the device->host copy of a tile's finished columns run under the next tile's compute. */
+int moe_run_band_to_host(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t in_row_stride, int planes,
+                         const MoePlan* plan, int row_lo, int row_hi, void* host_out, int bits_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,8 @@ SYMBOLS = {
   'moe_to_planar_f16': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
   'moe_to_output': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
   'moe_enhance_host': (_i, [_vp, _vp, _i, _plan, _vp, _i, _vp]),
+  'moe_enhance_host_c': (_i, [_vp, _vp, _i, _i, _plan, _vp, _i, _vp]),
+  'moe_run_band_to_host': (_i, [_vp, _vp, _i64, _i64, _i, _plan, _i, _i, _vp, _i, _vp]),
 }
 
 _lib = None

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -70,7 +71,11 @@ struct MoeEngine {
   bool arsb_attr_set = false;
   int bias_fused = 0;      // 1 = biased convolutions round once, q(conv + bias): the half model executed on the CPU (goldens); 0 = the GPU's two ops
   int static_sched = 0;    // 1 = pair kernels deal their items round-robin instead of drawing them (conv_pair.cuh, item scheduler)
-  int* d_sched = nullptr;  // the item scheduler's counters (kSchedInts ints, zero between launches)
+  // the item scheduler's counters: a ring of kSchedRing blocks of kSchedInts ints, one block per pair-kernel launch (the
+  // kernel's last pair zeroes its block again), so launches on DIFFERENT streams never draw each other's items
+  int* d_sched = nullptr;
+  std::atomic<uint32_t> sched_seq{0};
+  std::mutex host_mutex;   // moe_enhance_host: the engine-owned staging buffers serve one call at a time
   unsigned long long* dbg = nullptr;   // moe_engine_debug_buffer: per-pair {start ns, end ns, SM id, items} of the LAST pair-kernel launch
   bool pair_head_attr_set = false;
   bool pair_trunk_attr_set = false;
@@ -78,8 +83,8 @@ struct MoeEngine {
   bool profiling = false;
   struct Span { int cls; cudaEvent_t a, b; double work; };
   std::vector<Span> spans;
-  double prof_ms[4] = {0, 0, 0, 0}, prof_work[4] = {0, 0, 0, 0};
-  int64_t prof_n[4] = {0, 0, 0, 0};
+  double prof_ms[MOE_PROFILE_CLASSES] = {0}, prof_work[MOE_PROFILE_CLASSES] = {0};
+  int64_t prof_n[MOE_PROFILE_CLASSES] = {0};
   // grown-on-demand device buffers of moe_enhance_host: raw in, planar in, canvas, raw out, workspace
   cudaStream_t copy_stream = nullptr;   // moe_enhance_host: conversion + device->host copy of finished canvas columns
   cudaEvent_t copy_event = nullptr;
@@ -97,7 +102,6 @@ struct MoeModel {
   const uint8_t* up_img[8] = {nullptr};     // [4*branch + stage]
   const float* up_bias[8] = {nullptr};
   const float* frm[3] = {nullptr, nullptr, nullptr};   // MoeNet_lite2's FRM gates
-  float* d_frm_ws = nullptr;                 // partial sums + gates of the FRM reduction
   const float* head_w[2] = {nullptr, nullptr};
   uint8_t* d_head_img = nullptr;   // [2][16 rows][128 B] swizzled fp16 image of the two head filters (head_tc.cuh)
 };
@@ -127,6 +131,10 @@ struct Timed {
   }
   ~Timed() { if (idx >= 0) cudaEventRecord(e->spans[idx].b, st); }
 };
+
+constexpr uint32_t kSchedRing = 512;           // pair-kernel launches that may be in flight at once across all streams of an engine
+constexpr uint32_t kSchedStride = 32;          // ints per block (kSchedInts = 17, padded to a 128-byte line)
+int* next_sched_block(MoeEngine* e) { return e->d_sched + (e->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedRing) * kSchedStride; }
 
 int check_launch(MoeEngine* e, const char* what) {
   cudaError_t err = cudaPeekAtLastError();
@@ -173,7 +181,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   ConvParams p{};
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
   p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param; p.center_only = center_only;
-  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg; p.bias_fused = e->bias_fused;
+  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.bias_fused = e->bias_fused;
   // algorithmic FLOPs: 2 * taps * Cin * Cout per input pixel (padded channels are not counted)
   Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
   if (e->simt) {
@@ -282,9 +290,9 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   ArsbParams ap{};
   ConvParams& p = ap.c;
   p.w_img = w1_img; p.in = in; p.out = out; p.N = N; p.H = H; p.W = W; p.r = 1; p.epi = EPI_PRELU; p.param = slope;
-  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg;
+  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg;
   ap.w2_img = w2_img; ap.scale = scale;
-  Timed timed(e, st, 1, 2 * 2.0 * 9 * e->cur_feat * static_cast<double>(e->cur_feat) * N * H * W);   // both convolutions
+  Timed timed(e, st, 4, 2 * 2.0 * 9 * e->cur_feat * static_cast<double>(e->cur_feat) * N * H * W);   // both convolutions
   const int npairs_max = e->sm_count / 2;
   const int strips1 = (W + kArsbStripW - 1) / kArsbStripW;
   p.strips = (strips1 + 1) / 2;                                // strip PAIRS of 2 x 126 px
@@ -323,9 +331,9 @@ int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
   p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
-  p.dynamic = !e->static_sched; p.sched = e->d_sched; p.dbg = e->dbg; p.bias_fused = e->bias_fused;
+  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.bias_fused = e->bias_fused;
   hp.head_img = head_img; hp.hbuf = hbuf; hp.ebuf = ebuf;
-  Timed timed(e, st, 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
+  Timed timed(e, st, 5, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
   const int npairs_max = (e->sm_count / 2) & ~1;
   const int strips1 = (W + kStripW - 1) / kStripW;
   p.strips = (strips1 + 1) / 2;
@@ -438,6 +446,12 @@ size_t tile_units(const MoeModel* m) {
   return 4 + stage_units(m) + fin;
 }
 
+// MoeNet_lite2's FRM reduction (partial sums per plane + gates) lives behind the tile's activation buffers in the CALLER's
+// workspace, so two calls on two streams with two workspaces never share it
+size_t frm_bytes(const MoeModel* m, int planes) {
+  return m->arch == MOE_ARCH_LITE ? align_up((static_cast<size_t>(kFrmBlocks) + 1) * 64 * sizeof(float) * planes, 1024) : 0;
+}
+
 int validate_plan(const MoeModel* m, const MoePlan* pl, int planes, int row_lo, int row_hi) {
   if (!m || !pl || !pl->tiles || pl->n_tiles <= 0) return fail(MOE_ERR_INVALID, "null model or empty plan");
   if (pl->scale != m->scale) return fail(MOE_ERR_INVALID, "plan scale %d does not match model scale %d", pl->scale, m->scale);
@@ -489,7 +503,9 @@ int moe_engine_create(int device_id, MoeEngine** out)
     return fail(MOE_ERR_CUDA, "driver has no cuTensorMapEncodeTiled");
   }
   e->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (cudaMalloc(&e->d_sched, kSchedInts * sizeof(int)) != cudaSuccess || cudaMemset(e->d_sched, 0, kSchedInts * sizeof(int)) != cudaSuccess) {
+  static_assert(kSchedInts <= kSchedStride, "scheduler block too small");
+  if (cudaMalloc(&e->d_sched, kSchedRing * kSchedStride * sizeof(int)) != cudaSuccess ||
+      cudaMemset(e->d_sched, 0, kSchedRing * kSchedStride * sizeof(int)) != cudaSuccess) {
     cudaGetLastError();
     if (e->d_sched) cudaFree(e->d_sched);
     delete e;
@@ -521,7 +537,7 @@ int moe_engine_profile(MoeEngine* e, int enable)
   return MOE_OK;
 }
 
-int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t launches[4])
+int moe_engine_profile_read(MoeEngine* e, double ms[MOE_PROFILE_CLASSES], double work[MOE_PROFILE_CLASSES], int64_t launches[MOE_PROFILE_CLASSES])
 {
   if (!e || !ms || !work || !launches) return fail(MOE_ERR_INVALID, "null argument");
   Guard g(e->device);
@@ -533,7 +549,7 @@ int moe_engine_profile_read(MoeEngine* e, double ms[4], double work[4], int64_t 
     cudaEventDestroy(s.a); cudaEventDestroy(s.b);
   }
   e->spans.clear();
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < MOE_PROFILE_CLASSES; ++i) {
     ms[i] = e->prof_ms[i]; work[i] = e->prof_work[i]; launches[i] = e->prof_n[i];
     e->prof_ms[i] = e->prof_work[i] = 0; e->prof_n[i] = 0;
   }
@@ -611,10 +627,6 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
   for (int l = 0; l < (lite ? 7 : 13) && complete; ++l) complete = m->trunk_img[l] != nullptr;
   for (int b = 0; b < 2 && complete; ++b)
     for (uint32_t s = 0; s < h.n_up && complete; ++s) complete = m->up_img[4 * b + s] && m->up_bias[4 * b + s];
-  if (complete && lite && cudaMalloc(&m->d_frm_ws, (static_cast<size_t>(kFrmBlocks) + 1) * 64 * 4 * 256) != cudaSuccess) {   // up to 256 planes
-    cudaGetLastError(); cudaFree(m->d_blob); delete m;
-    return fail(MOE_ERR_NOMEM, "FRM workspace allocation failed");
-  }
   if (!complete) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "blob is missing sections"); }
   {
     // head filters as a K-major SWIZZLE_128B B operand: row = tap (9 of 16 used), 64 input channels
@@ -641,7 +653,6 @@ void moe_model_free(MoeModel* m)
   Guard g(m->e->device);
   if (m->d_blob) cudaFree(m->d_blob);
   if (m->d_head_img) cudaFree(m->d_head_img);
-  if (m->d_frm_ws) cudaFree(m->d_frm_ws);
   delete m;
 }
 
@@ -656,7 +667,7 @@ size_t moe_plan_workspace_bytes(const MoeModel* m, int planes, const MoePlan* pl
     if (!g.active) continue;
     if (m->arch == MOE_ARCH_LITE) g.H = plan->tiles[i].bottom - plan->tiles[i].top;
     const size_t unit = align_up(static_cast<size_t>(planes) * g.H * g.W * 128, 1024);
-    worst = std::max(worst, unit * tile_units(m));
+    worst = std::max(worst, unit * tile_units(m) + frm_bytes(m, planes));
   }
   return worst + 1024;
 }
@@ -737,14 +748,14 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, N, H, W, 1, EPI_PLAIN, 0.f, one_by_one)) != MOE_OK) return rc;   // conv_input2
     if (m->arch == MOE_ARCH_LITE) {
       // three LB blocks: t = FRM(conv_2(PReLU(conv_1(t)))) + t                  MoeNet_lite2.py:7-20, models.py:270-287
-      if (N > 256) return fail(MOE_ERR_INVALID, "MoeNet_lite2: more than 256 planes per call");
-      float* partial = m->d_frm_ws;
-      float* gate = m->d_frm_ws + static_cast<size_t>(kFrmBlocks) * 64 * 256;
+      float* partial = reinterpret_cast<float*>(ws + tile_units(m) * unit);
+      float* gate = partial + static_cast<size_t>(kFrmBlocks) * 64 * N;
       const int64_t px = static_cast<int64_t>(H) * W;
       for (int b = 0; b < 3; ++b) {
         const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
         if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
         if ((rc = launch_conv(e, st, bufM, bufC, nullptr, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
+        Timed timed(e, st, 6, static_cast<double>(N) * px * 128 * 4);               // bytes: v read twice, t read and written
         frm_partial_kernel<<<dim3(kFrmBlocks, N), 256, 0, st>>>(bufC, partial, px);
         if ((rc = check_launch(e, "frm_partial_kernel")) != MOE_OK) return rc;
         frm_gate_kernel<<<N, 64, 0, st>>>(partial, m->frm[b], gate, 1.0f / static_cast<float>(px), e->bias_fused);
@@ -911,25 +922,25 @@ static int ensure_buf(MoeEngine* e, int i, size_t bytes)
 namespace {
 // toFloat + toOutput on a column range [x0,x1) of the canvas (same arithmetic as to_output_kernel)
 template <typename T>
-__global__ void to_output_cols_kernel(const __half* src, int h, int w, int x0, int x1, float quant, T* dst)
+__global__ void to_output_cols_kernel(const __half* src, size_t plane, int h, int w, int c, int x0, int x1, float quant, T* dst)
 {
   const int cols = x1 - x0;
   const size_t total = static_cast<size_t>(h) * cols;
-  const size_t plane = static_cast<size_t>(h) * w;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t y = i / cols, px = y * w + x0 + (i - y * cols);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
+    for (int ch = 0; ch < c; ++ch) {
       float v = __half2float(src[ch * plane + px]) * quant;
       v = fminf(fmaxf(v, 0.f), quant - 1.f);
-      dst[px * 3 + ch] = static_cast<T>(v);
+      dst[px * c + ch] = static_cast<T>(v);
     }
   }
 }
 
+// `canvas` points at canvas row `row_lo` of plane 0 (planes `plane` halfs apart), d_out / host_out at row `row_lo` of the
+// interleaved result: the overlap works on a row band of the frame (the whole frame at N = 1)
 struct OverlapCtx {
   MoeEngine* e; const MoePlan* plan; cudaStream_t compute, copy; cudaEvent_t ev;
-  const __half* canvas; uint8_t* d_out; uint8_t* host_out; int bits_out; int done_x; int row_lo, row_hi;
+  const __half* canvas; size_t plane; uint8_t* d_out; uint8_t* host_out; int bits_out; int done_x; int row_lo, row_hi; int channels;
 };
 
 // convert + copy the canvas columns [c->done_x, x_end) once everything enqueued so far on the compute stream is done
@@ -937,20 +948,20 @@ int flush_columns(OverlapCtx* c, int x_end)
 {
   if (x_end <= c->done_x) return MOE_OK;
   const MoePlan* pl = c->plan;
-  const int bpp = c->bits_out <= 8 ? 1 : 2;
+  const int bpp = c->bits_out <= 8 ? 1 : 2, rows = c->row_hi - c->row_lo;
   MOE_CUDA(cudaEventRecord(c->ev, c->compute));
   MOE_CUDA(cudaStreamWaitEvent(c->copy, c->ev, 0));
-  const int64_t threads = static_cast<int64_t>(pl->out_h) * (x_end - c->done_x);
+  const int64_t threads = static_cast<int64_t>(rows) * (x_end - c->done_x);
   const int grid = grid_for(threads, 256, c->e->sm_count);
   const float quant = static_cast<float>(1 << c->bits_out);
   if (bpp == 1)
-    to_output_cols_kernel<uint8_t><<<grid, 256, 0, c->copy>>>(c->canvas, pl->out_h, pl->out_w, c->done_x, x_end, quant, c->d_out);
+    to_output_cols_kernel<uint8_t><<<grid, 256, 0, c->copy>>>(c->canvas, c->plane, rows, pl->out_w, c->channels, c->done_x, x_end, quant, c->d_out);
   else
-    to_output_cols_kernel<uint16_t><<<grid, 256, 0, c->copy>>>(c->canvas, pl->out_h, pl->out_w, c->done_x, x_end, quant, reinterpret_cast<uint16_t*>(c->d_out));
+    to_output_cols_kernel<uint16_t><<<grid, 256, 0, c->copy>>>(c->canvas, c->plane, rows, pl->out_w, c->channels, c->done_x, x_end, quant, reinterpret_cast<uint16_t*>(c->d_out));
   int rc = check_launch(c->e, "to_output_cols_kernel");
   if (rc != MOE_OK) return rc;
-  const size_t pitch = static_cast<size_t>(pl->out_w) * 3 * bpp, off = static_cast<size_t>(c->done_x) * 3 * bpp;
-  MOE_CUDA(cudaMemcpy2DAsync(c->host_out + off, pitch, c->d_out + off, pitch, static_cast<size_t>(x_end - c->done_x) * 3 * bpp, pl->out_h,
+  const size_t pitch = static_cast<size_t>(pl->out_w) * c->channels * bpp, off = static_cast<size_t>(c->done_x) * c->channels * bpp;
+  MOE_CUDA(cudaMemcpy2DAsync(c->host_out + off, pitch, c->d_out + off, pitch, static_cast<size_t>(x_end - c->done_x) * c->channels * bpp, rows,
                              cudaMemcpyDeviceToHost, c->copy));
   c->done_x = x_end;
   return MOE_OK;
@@ -968,23 +979,31 @@ int overlap_after_tile(int ti, void* ctx)
 
 extern "C" {
 
-int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePlan* plan, void* host_out, int bits_out, void* stream)
+int moe_enhance_host_c(MoeModel* m, const void* host_in, int bits_in, int channels, const MoePlan* plan, void* host_out, int bits_out, void* stream)
 {
-  int rc = validate_plan(m, plan, 3, 0, plan ? plan->out_h : 0);
+  if (channels != 1 && channels != 3 && channels != 4) return fail(MOE_ERR_INVALID, "frames have 1, 3 or 4 channels, got %d", channels);
+  // the reference's SR path upscales an alpha plane like a colour plane (a 4th batch element); its RGBFilter (DN) strips the
+  // alpha plane, filters the colour planes and re-attaches it untouched (imageProcess.py:370-377)
+  const bool alpha_bypass = m && m->scale == 1 && channels == 4;
+  const int net_planes = alpha_bypass ? 3 : channels;
+  int rc = validate_plan(m, plan, net_planes, 0, plan ? plan->out_h : 0);
   if (rc != MOE_OK) return rc;
   if (!host_in || !host_out) return fail(MOE_ERR_INVALID, "null host buffer");
   if (bits_in < 1 || bits_in > 16 || bits_out < 1 || bits_out > 16) return fail(MOE_ERR_INVALID, "bad bit depth");
   MoeEngine* e = m->e;
   Guard guard(e->device);
+  std::lock_guard<std::mutex> lock(e->host_mutex);      // the engine-owned staging buffers below serve one call at a time
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t ipx = static_cast<size_t>(plan->in_h) * plan->in_w, opx = static_cast<size_t>(plan->out_h) * plan->out_w;
-  const size_t in_raw = ipx * 3 * (bits_in <= 8 ? 1 : 2), out_raw = opx * 3 * (bits_out <= 8 ? 1 : 2);
-  const size_t wsb = moe_plan_workspace_bytes(m, 3, plan, 0, plan->out_h);
-  if ((rc = ensure_buf(e, 0, in_raw)) || (rc = ensure_buf(e, 1, ipx * 3 * 2)) || (rc = ensure_buf(e, 2, opx * 3 * 2)) ||
+  const size_t in_raw = ipx * channels * (bits_in <= 8 ? 1 : 2), out_raw = opx * channels * (bits_out <= 8 ? 1 : 2);
+  const size_t wsb = moe_plan_workspace_bytes(m, net_planes, plan, 0, plan->out_h);
+  if ((rc = ensure_buf(e, 0, in_raw)) || (rc = ensure_buf(e, 1, ipx * channels * 2)) || (rc = ensure_buf(e, 2, opx * channels * 2)) ||
       (rc = ensure_buf(e, 3, out_raw)) || (rc = ensure_buf(e, 4, wsb)))
     return rc;
   MOE_CUDA(cudaMemcpyAsync(e->buf[0], host_in, in_raw, cudaMemcpyHostToDevice, st));
-  if ((rc = moe_to_planar_f16(e, e->buf[0], bits_in, plan->in_h, plan->in_w, 3, 0, e->buf[1], st)) != MOE_OK) return rc;
+  if ((rc = moe_to_planar_f16(e, e->buf[0], bits_in, plan->in_h, plan->in_w, channels, 0, e->buf[1], st)) != MOE_OK) return rc;
+  if (alpha_bypass)
+    MOE_CUDA(cudaMemcpyAsync(static_cast<__half*>(e->buf[2]) + 3 * opx, static_cast<const __half*>(e->buf[1]) + 3 * ipx, ipx * 2, cudaMemcpyDeviceToDevice, st));
   // One row of tiles (the reference's plan for big frames: column strips): a tile's columns are final as soon as the
   // NEXT tile's kept region starts, so their conversion and device->host copy run on a second stream under the next
   // tile's compute.  Several tile rows: convert and copy everything at the end.
@@ -994,10 +1013,49 @@ int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePla
     MOE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     MOE_CUDA(cudaEventCreateWithFlags(&e->copy_event, cudaEventDisableTiming));
   }
-  OverlapCtx ctx{e, plan, st, e->copy_stream, e->copy_event, static_cast<const __half*>(e->buf[2]), static_cast<uint8_t*>(e->buf[3]),
-                 static_cast<uint8_t*>(host_out), bits_out, 0, 0, plan->out_h};
-  if ((rc = run_plan_core(m, e->buf[1], static_cast<int64_t>(ipx), plan->in_w, 3, e->buf[2], static_cast<int64_t>(opx), plan->out_w,
+  OverlapCtx ctx{e, plan, st, e->copy_stream, e->copy_event, static_cast<const __half*>(e->buf[2]), opx, static_cast<uint8_t*>(e->buf[3]),
+                 static_cast<uint8_t*>(host_out), bits_out, 0, 0, plan->out_h, channels};
+  if ((rc = run_plan_core(m, e->buf[1], static_cast<int64_t>(ipx), plan->in_w, net_planes, e->buf[2], static_cast<int64_t>(opx), plan->out_w,
                           plan, 0, plan->out_h, e->buf[4], e->cap[4], st, one_row ? overlap_after_tile : nullptr, &ctx)) != MOE_OK) return rc;
+  if ((rc = flush_columns(&ctx, plan->out_w)) != MOE_OK) return rc;
+  MOE_CUDA(cudaStreamSynchronize(e->copy_stream));
+  MOE_CUDA(cudaStreamSynchronize(st));
+  return MOE_OK;
+}
+
+int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePlan* plan, void* host_out, int bits_out, void* stream)
+{
+  return moe_enhance_host_c(m, host_in, bits_in, 3, plan, host_out, bits_out, stream);
+}
+
+int moe_run_band_to_host(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t in_row_stride, int planes, const MoePlan* plan,
+                         int row_lo, int row_hi, void* host_out, int bits_out, void* stream)
+{
+  int rc = validate_plan(m, plan, planes, row_lo, row_hi);
+  if (rc != MOE_OK) return rc;
+  if (!in || !host_out) return fail(MOE_ERR_INVALID, "null buffer");
+  if (bits_out < 1 || bits_out > 16) return fail(MOE_ERR_INVALID, "bad bit depth");
+  MoeEngine* e = m->e;
+  Guard guard(e->device);
+  std::lock_guard<std::mutex> lock(e->host_mutex);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = row_hi - row_lo, bpp = bits_out <= 8 ? 1 : 2;
+  const size_t band_px = static_cast<size_t>(rows) * plan->out_w;
+  const size_t wsb = moe_plan_workspace_bytes(m, planes, plan, row_lo, row_hi);
+  if ((rc = ensure_buf(e, 2, band_px * planes * 2)) || (rc = ensure_buf(e, 3, band_px * planes * bpp)) || (rc = ensure_buf(e, 4, wsb))) return rc;
+  bool one_row = true;
+  for (int i = 0; i < plan->n_tiles; ++i) one_row = one_row && plan->tiles[i].top == 0 && plan->tiles[i].bsc == plan->out_h;
+  if (!e->copy_stream) {
+    MOE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    MOE_CUDA(cudaEventCreateWithFlags(&e->copy_event, cudaEventDisableTiming));
+  }
+  // the band canvas holds rows [row_lo, row_hi) only: frame row r lives at band row r - row_lo (same strides, shifted base)
+  __half* band = static_cast<__half*>(e->buf[2]);
+  __half* base = band - static_cast<int64_t>(row_lo) * plan->out_w;
+  uint8_t* host_band = static_cast<uint8_t*>(host_out) + static_cast<size_t>(row_lo) * plan->out_w * planes * bpp;
+  OverlapCtx ctx{e, plan, st, e->copy_stream, e->copy_event, band, band_px, static_cast<uint8_t*>(e->buf[3]), host_band, bits_out, 0, row_lo, row_hi, planes};
+  if ((rc = run_plan_core(m, in, in_plane_stride, in_row_stride, planes, base, static_cast<int64_t>(band_px), plan->out_w, plan, row_lo, row_hi,
+                          e->buf[4], e->cap[4], st, one_row ? overlap_after_tile : nullptr, &ctx)) != MOE_OK) return rc;
   if ((rc = flush_columns(&ctx, plan->out_w)) != MOE_OK) return rc;
   MOE_CUDA(cudaStreamSynchronize(e->copy_stream));
   MOE_CUDA(cudaStreamSynchronize(st));

@@ -54,12 +54,18 @@ class Engine:
   def profile(self, enable):
     _lib.check(self.lib.moe_engine_profile(self.handle, int(bool(enable))))
 
+  PROFILE_CLASSES = ('conv_input', 'conv_trunk', 'head', 'conv_up', 'arsb', 'conv_up_head', 'frm', 'reserved')
+
   def profile_read(self):
-    """-> {class: (ms, work, launches)} for conv_input / conv3x3 / head, and resets the counters"""
-    ms, work, n = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_int64 * 4)()
+    """-> {class: (ms, algorithmic work, launches)} per kernel class (include/moephoto_b200.h) plus the sums 'conv3x3' (every
+    tensor-core convolution), 'trunk' (conv_trunk + arsb) and 'up' (conv_up + conv_up_head); resets the counters"""
+    n_cls = len(self.PROFILE_CLASSES)
+    ms, work, n = (ctypes.c_double * n_cls)(), (ctypes.c_double * n_cls)(), (ctypes.c_int64 * n_cls)()
     _lib.check(self.lib.moe_engine_profile_read(self.handle, ms, work, n))
-    d = {k: (ms[i], work[i], n[i]) for i, k in enumerate(('conv_input', 'conv_trunk', 'head', 'conv_up'))}
-    d['conv3x3'] = tuple(a + b for a, b in zip(d['conv_trunk'], d['conv_up']))      # every 3x3 tensor-core convolution
+    d = {k: (ms[i], work[i], n[i]) for i, k in enumerate(self.PROFILE_CLASSES)}
+    add = lambda *ks: tuple(sum(d[k][j] for k in ks) for j in range(3))
+    d['trunk'], d['up'] = add('conv_trunk', 'arsb'), add('conv_up', 'conv_up_head')
+    d['conv3x3'] = add('conv_trunk', 'arsb', 'conv_up', 'conv_up_head')
     return d
 
   def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False, static_sched=False, bias_fused=False, no_arsb=False):
@@ -314,8 +320,10 @@ def prepareOpt(opt, shape):
 # ------------------------------------------------------------------------------------------------
 # doCrop
 # ------------------------------------------------------------------------------------------------
-def run_plan(model, x, plan, out=None, rows=None):
-  """x: (planes,H,W) CUDA tensor -> canvas (planes, s*H, s*W) fp16.  `rows` = (lo,hi) canvas row window."""
+def run_plan(model, x, plan, out=None, rows=None, workspace=None):
+  """x: (planes,H,W) CUDA tensor -> canvas (planes, s*H, s*W) fp16.  `rows` = (lo,hi) canvas row window.  `workspace`: a uint8
+  CUDA tensor of at least moe_plan_workspace_bytes — calls that overlap on different streams need one each (default: the
+  engine's own, for the single-stream use of the reference's worker)."""
   if not x.is_cuda:
     raise RuntimeError('moephoto_b200 has no CPU path: the input tensor must live on the GPU')
   if x.dtype != torch.half:
@@ -326,14 +334,16 @@ def run_plan(model, x, plan, out=None, rows=None):
   if (h, w) != (plan.in_h, plan.in_w):
     raise ValueError('plan was made for {}x{}, got {}x{}'.format(plan.in_h, plan.in_w, h, w))
   eng = model.engine
-  dev = x.device.index
+  dev = eng.device_id          # the launch stream is the engine's device's (x / out may be peer-mapped memory of another GPU)
   if out is None:
     out = torch.empty((planes, plan.out_h, plan.out_w), dtype=torch.half, device=x.device)
   lo, hi = (0, plan.out_h) if rows is None else rows
   need = eng.lib.moe_plan_workspace_bytes(model.handle, planes, ctypes.byref(plan.c), lo, hi)
   if need == 0:
     _lib.check(_lib.MOE_ERR_INVALID)
-  ws = eng.get_workspace(need)
+  ws = eng.get_workspace(need) if workspace is None else workspace
+  if ws.numel() < need:
+    raise MemoryError('workspace of {} bytes is too small (need {})'.format(ws.numel(), need))
   _lib.check(eng.lib.moe_run_plan(model.handle, ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), planes,
                                   ctypes.c_void_p(out.data_ptr()), out.stride(0), out.stride(1),
                                   ctypes.byref(plan.c), lo, hi, ctypes.c_void_p(ws.data_ptr()), ws.numel(),

@@ -568,3 +568,59 @@ def test_fused_residual_block_is_bit_identical_to_its_two_launch_form(engine, ke
         assert torch.equal(y, y2)
     finally:
         config.freeMemOverride = None
+
+
+def test_two_streams_share_an_engine(engine):
+    """every pair-kernel launch draws its items from its own counter block and the FRM scratch lives in the caller's
+    workspace, so two plans may run concurrently on two streams of one engine (two workspaces): results equal the serial ones"""
+    from moephoto_b200 import imageProcess as IP
+    from moephoto_b200.config import config
+    import ctypes
+    oa, ol = _sr_opt('a4', 4, crop=96), _sr_opt('lite2', 2, crop=64)
+    try:
+        g = torch.Generator().manual_seed(31)
+        xa, xl = torch.rand(3, 300, 520, generator=g).half().cuda(), torch.rand(3, 200, 300, generator=g).half().cuda()
+        want_a, want_l = IP.doCrop(oa, xa), IP.doCrop(ol, xl)
+        torch.cuda.synchronize()
+        need = lambda o, x: engine.lib.moe_plan_workspace_bytes(o.modelCached.handle, 3, ctypes.byref(o.plan.c), 0, o.plan.out_h)
+        wa = torch.empty(need(oa, xa), dtype=torch.uint8, device='cuda')
+        wl = torch.empty(need(ol, xl), dtype=torch.uint8, device='cuda')
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        for _ in range(3):
+            got_a, got_l = torch.empty_like(want_a), torch.empty_like(want_l)
+            with torch.cuda.stream(s1):
+                for _ in range(2):
+                    IP.run_plan(oa.modelCached, xa, oa.plan, got_a, workspace=wa)
+            with torch.cuda.stream(s2):
+                for _ in range(4):
+                    IP.run_plan(ol.modelCached, xl, ol.plan, got_l, workspace=wl)
+            torch.cuda.synchronize()
+            assert torch.equal(got_a, want_a) and torch.equal(got_l, want_l)
+    finally:
+        config.freeMemOverride = None
+
+
+@pytest.mark.parametrize('channels', [1, 4])
+def test_host_buffer_entry_point_grey_and_rgba(engine, channels):
+    """moe_enhance_host_c: a grey frame, and an RGBA frame whose alpha plane the SR model upscales like a colour plane
+    (runSR.py:39-40) while the DN model passes it through (_RGBFilter, imageProcess.py:370-377) — equal to the API path"""
+    from moephoto_b200 import _lib, runDN, imageProcess as IP
+    from moephoto_b200.config import config
+    opt = _sr_opt('a2', 2, crop=64, ram=int(4e9))
+    try:
+        img = np.random.default_rng(40 + channels).integers(0, 256, (70, 90, channels), dtype=np.uint8)
+        want = IP.toOutput(8)(IP.doCrop(opt, IP.toTorch(8)(img)))
+        out = np.empty((140, 180, channels), dtype=np.uint8)
+        _lib.check(engine.lib.moe_enhance_host_c(opt.modelCached.handle, img.ctypes.data_as(ctypes.c_void_p), 8, channels, ctypes.byref(opt.plan.c),
+                                                 out.ctypes.data_as(ctypes.c_void_p), 8, None))
+        assert np.array_equal(out, want)
+        if channels == 4:
+            config.freeMemOverride, config.crop_dn = int(4e9), 48
+            odn = runDN.getOpt({'model': 'lite15'}, weights=H.load_weights('dn_lite15'))
+            want = IP.toOutput(8)(IP.RGBFilter(odn)(IP.toTorch(8)(img)))
+            out = np.empty((70, 90, 4), dtype=np.uint8)
+            _lib.check(engine.lib.moe_enhance_host_c(odn.modelCached.handle, img.ctypes.data_as(ctypes.c_void_p), 8, 4, ctypes.byref(odn.plan.c),
+                                                     out.ctypes.data_as(ctypes.c_void_p), 8, None))
+            assert np.array_equal(out, want) and np.array_equal(out[:, :, 3], img[:, :, 3])
+    finally:
+        config.freeMemOverride, config.crop_dn = None, 'auto'
