@@ -112,6 +112,50 @@ class FrameBatcher:
       yield from self._collect(self.stages[k % 2], copy)
 
 
+class _PipeFrames:
+  """the frames of a raw byte pipe as a lazily growing sequence (what FrameBatcher.process indexes)"""
+
+  def __init__(self, read, height, width, bit_depth, limit=None):
+    self.read, self.h, self.w, self.limit = read, height, width, limit
+    self.dtype = np.uint8 if bit_depth <= 8 else np.uint16
+    self.nbytes = height * width * 3 * (1 if bit_depth <= 8 else 2)
+    self.frames, self.eof = [], False
+
+  def fill(self, n):
+    """read until n frames are buffered or the pipe ends (an empty or short read: video.py:351-353)"""
+    while not self.eof and len(self.frames) < n and (self.limit is None or len(self.frames) < self.limit):
+      raw = self.read(self.nbytes)
+      if raw is None or len(raw) < self.nbytes:
+        self.eof = True
+        break
+      self.frames.append(np.frombuffer(raw, dtype=self.dtype).reshape(self.h, self.w, 3))
+    return len(self.frames)
+
+
+def pipe_loop(read, write, height, width, opts, bit_depth=16, swap_rb=True, batch=None, stop=None, should_stop=None):
+  """The reference's frame loop (video.py:339-360: `raw_image = procIn.stdout.read(frameBytes)` -> process((raw, h, w)) ->
+  `procOut.stdin.write(buffer)`) with B frames per engine call instead of one.  `read(nbytes)` and `write(bytes)` are the two pipe
+  ends (ffmpeg's stdout / stdin in MoePhoto; any callables here); frames are bgr48le (bit_depth 16) or bgr24 as MoePhoto's ffmpeg
+  command lines produce them, `opts` the Options of the step chain (toNumPy -> toTorch -> DN / SR ... -> toOutput -> BGR -> toBuffer
+  collapse into the batcher's two conversion kernels).  Frames are written in order; returns the number of frames processed.
+  `should_stop()` is polled once per batch (context.stopFlag, video.py:350)."""
+  src = _PipeFrames(read, height, width, bit_depth, stop)
+  if src.fill(1) == 0:
+    return 0
+  fb = FrameBatcher(opts, height, width, bit_depth, swap_rb, batch)
+  done = 0
+  while True:
+    n = src.fill(done + fb.batch)
+    if n == done or (should_stop is not None and should_stop()):
+      break
+    for _, frame in fb.process(src.frames[done:n], copy=False):
+      write(frame.tobytes())
+    for i in range(done, n):
+      src.frames[i] = None                                                     # drop the input bytes of finished frames
+    done = n
+  return done
+
+
 def process_frames(frames, opts, bit_depth=16, swap_rb=True, batch=None, rank=0, world=1):
   """one-shot convenience around FrameBatcher: frames = sequence of HWC integer arrays (bgr48le / bgr24 as video.py
   pipes them when swap_rb); opts = the Options of the step chain in order; yields (index, HWC integer frame)"""

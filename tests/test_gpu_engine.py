@@ -624,3 +624,32 @@ def test_host_buffer_entry_point_grey_and_rgba(engine, channels):
             assert np.array_equal(out, want) and np.array_equal(out[:, :, 3], img[:, :, 3])
     finally:
         config.freeMemOverride, config.crop_dn = None, 'auto'
+
+
+def test_video_pipe_loop_equals_the_reference_frame_loop(engine):
+    """moephoto_b200.video.pipe_loop sits where the reference's loop sits (video.py:339-360): raw bgr48le bytes from a pipe
+    read() -> batches of frames through DN -> SR on the engine -> bytes to a pipe write().  Against the per-frame chain of the
+    reference's steps (toNumPy -> toTorch(16) -> RGBFilter -> sr -> toOutput(16) -> BGR -> toBuffer), byte for byte, with a
+    frame count that is not a multiple of the batch and a short read ending the stream"""
+    import io
+    from moephoto_b200 import runSR, runDN, imageProcess as IP, video
+    from moephoto_b200.config import config
+    rng = np.random.default_rng(8)
+    h, w, n = 40, 56, 7
+    raw_frames = [rng.integers(0, 65536, (h, w, 3), dtype=np.uint16).tobytes() for _ in range(n)]
+    config.freeMemOverride, config.crop_dn, config.crop_sr = int(4e9), 32, 32
+    try:
+        odn = runDN.getOpt({'model': 'lite15'}, weights=H.load_weights('dn_lite15'))
+        osr = runSR.getOpt({'model': 'a', 'scale': 2}, weights=H.load_weights('a2'))
+        want = b''
+        for raw in raw_frames:                                         # the reference's loop: one frame per iteration
+            im = IP.toNumPy(16)((raw, h, w))
+            x = IP.toTorch(16, swapRB=True)(im)
+            want += IP.toBuffer(16)(IP.toOutput(16, swapRB=True)(runSR.sr(osr)(IP.RGBFilter(odn)(x))))
+        pipe_in = io.BytesIO(b''.join(raw_frames) + b'\x00' * 100)      # a truncated last read ends the stream
+        pipe_out = io.BytesIO()
+        done = video.pipe_loop(pipe_in.read, pipe_out.write, h, w, [odn, osr], bit_depth=16, swap_rb=True, batch=3)
+        assert done == n and pipe_out.getvalue() == want
+        assert video.pipe_loop(io.BytesIO(b'').read, pipe_out.write, h, w, [odn, osr]) == 0
+    finally:
+        config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
