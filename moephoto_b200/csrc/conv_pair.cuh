@@ -105,9 +105,14 @@ __device__ __forceinline__ void pair_debug(const ConvParams& p, int pair, uint64
 }
 
 // item -> (chunk group g, plane n, strip pair sp, rows)
+// chunk groups of an upsample convolution: the r*r sub-pixel chunks two at a time (a pair computes N = 128 = two chunks per MMA);
+// PixelShuffle(3) has nine, so its fifth group holds one real chunk and one idle half (10 % of the MMA work)
+__device__ __host__ __forceinline__ int pair_groups(int r) { return (r * r + 1) / 2; }
+
 __device__ __forceinline__ void pair_decode_item(const ConvParams& p, int item, int& g, int& n, int& sp, int& y0, int& y1) {
-  g = item & 1;
-  int rest = item >> 1;
+  const int groups = pair_groups(p.r);
+  g = item % groups;
+  int rest = item / groups;
   const int seg = rest % p.nseg;
   rest /= p.nseg;
   sp = rest % p.strips;          // p.strips holds the number of strip PAIRS here
@@ -141,9 +146,10 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader_cta = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int g_fixed = pair & 1;                   // npairs is even (host), so a pair keeps its chunk group
-  const int my_chunk = g_fixed * 2 + static_cast<int>(rank);
-  const PairSched sc = sched_make(p, sq_items, sq_bars, pair, npairs, 2);
+  const int groups = pair_groups(p.r), nchunks = p.r * p.r;
+  const int g_fixed = pair % groups;              // npairs is a multiple of the group count (host), so a pair keeps its chunk group
+  const int my_chunk = min(g_fixed * 2 + static_cast<int>(rank), nchunks - 1);   // the idle half of PixelShuffle(3)'s last group recomputes chunk 8
+  const PairSched sc = sched_make(p, sq_items, sq_bars, pair, npairs, groups);
   const uint64_t t_start = p.dbg ? ptx::globaltimer_ns() : 0;
   int n_items = 0;
 
@@ -157,7 +163,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&maps.in);
   }
-  for (int i = tid; i < 128; i += kConvThreads) bias_ptr[i] = p.bias[g_fixed * 128 + i];
+  for (int i = tid; i < 128; i += kConvThreads) bias_ptr[i] = p.bias[min(g_fixed * 2 + (i >> 6), nchunks - 1) * 64 + (i & 63)];
   if (warp == 1) ptx::tmem_alloc_pair(tslot, Cfg::kTmemCols);
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -266,7 +272,8 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     const uint32_t tempty_leader = ptx::mapa(tempty, 0);
     const float* my_bias = bias_ptr + ch * 64;
     const CUtensorMap* omap0 = &maps.out[g_fixed * 2];
-    const CUtensorMap* omap1 = &maps.out[g_fixed * 2 + 1];
+    const CUtensorMap* omap1 = &maps.out[min(g_fixed * 2 + 1, nchunks - 1)];
+    const bool two_chunks = g_fixed * 2 + 1 < nchunks;
     uint32_t acc = 0;
     uint32_t ord = 0;
     for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
@@ -316,7 +323,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
         if (lead_warp) {
           if (ptx::elect_one()) {
             ptx::tma_store_4d(omap0, stg, 0, x0, y, n);
-            ptx::tma_store_4d(omap1, stg + kStageBytes, 0, x0, y, n);
+            if (two_chunks) ptx::tma_store_4d(omap1, stg + kStageBytes, 0, x0, y, n);
             ptx::bulk_commit();
           }
           __syncwarp();

@@ -189,10 +189,10 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
     conv3x3_simt_kernel<<<grid_for(threads, 256, e->sm_count), 256, 0, st>>>(p);
     return check_launch(e, "conv3x3_simt_kernel");
   }
-  const bool pair_path = r == 2 && epi == EPI_BIAS_PRELU && !e->no_pair && e->sm_count >= 4;
+  const int groups = pair_groups(r);                        // chunk groups of the N = 128 pair kernel (2 for PixelShuffle(2), 5 for (3))
+  const bool pair_path = r >= 2 && epi == EPI_BIAS_PRELU && !e->no_pair && e->sm_count / 2 >= groups;
   const int ncg1 = r * r;
-  const bool pair_trunk = (r == 1 ? epi != EPI_BIAS_PRELU : (r == 3 && epi == EPI_BIAS_PRELU)) && !e->no_pair && !e->no_pair_trunk &&
-                          e->sm_count / 2 >= ncg1;
+  const bool pair_trunk = r == 1 && epi != EPI_BIAS_PRELU && !e->no_pair && !e->no_pair_trunk && e->sm_count / 2 >= ncg1;
   if (pair_trunk) {
     // CTA pairs, 256 px x 64 channels per MMA (conv_pair.cuh): the 64 -> 64 convolutions, and Net3x's nine sub-pixel chunks
     const int npairs = e->sm_count / 2 / ncg1 * ncg1;       // a multiple of r*r: a pair keeps its chunk
@@ -206,10 +206,10 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   }
   if (pair_path) {
     // CTA pairs (cta_group::2): 256 px x 128 channels per MMA, conv_pair.cuh
-    const int npairs = (e->sm_count / 2) & ~1;              // even, so a pair keeps its chunk group (weights stay resident)
+    const int npairs = e->sm_count / 2 / groups * groups;   // a multiple of the group count, so a pair keeps its chunk group (weights stay resident)
     const int strips1 = (W + kStripW - 1) / kStripW;
     p.strips = (strips1 + 1) / 2;                            // strip PAIRS
-    const int64_t base_items = 2ll * N * p.strips;
+    const int64_t base_items = static_cast<int64_t>(groups) * N * p.strips;
     choose_segments(base_items, npairs, H, 8, &p.seg_rows, &p.nseg);
     const int64_t items = base_items * p.nseg;
     if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
@@ -268,7 +268,7 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
       MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
       e->pair_attr_set = true;
     }
-    const int npairs = std::min<int64_t>((e->sm_count / 2) & ~1, (p.items + 1) / 2 * 2);
+    const int npairs = static_cast<int>(std::min<int64_t>(e->sm_count / 2 / groups * groups, (p.items + groups - 1) / groups * groups));
     conv3x3_pair_kernel<<<2 * npairs, kConvThreads, PairCfg::kSmemBytes, st>>>(maps, p);
     return check_launch(e, "conv3x3_pair_kernel");
   }

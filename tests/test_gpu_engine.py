@@ -621,7 +621,7 @@ def test_host_buffer_entry_point_grey_and_rgba(engine, channels):
             out = np.empty((70, 90, 4), dtype=np.uint8)
             _lib.check(engine.lib.moe_enhance_host_c(odn.modelCached.handle, img.ctypes.data_as(ctypes.c_void_p), 8, 4, ctypes.byref(odn.plan.c),
                                                      out.ctypes.data_as(ctypes.c_void_p), 8, None))
-            assert np.array_equal(out, want) and np.array_equal(out[:, :, 3], img[:, :, 3])
+            assert np.array_equal(out, want)          # (alpha itself goes x/255 -> fp16 -> x256: 254 comes back as 255, in the reference too)
     finally:
         config.freeMemOverride, config.crop_dn = None, 'auto'
 
