@@ -117,9 +117,8 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tslot_ptr;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer: weights once, then the t rows of every item
+  ptx::grid_dep_launch();
+  if (warp == 0) {                                 // weights before the dependency wait (see conv3x3_pair_kernel)
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, 2 * Cfg::kWBytes);
       for (int tap = 0; tap < 9; ++tap) {      // output channels 32*rank .. +31 of every tap, both convolutions
@@ -128,6 +127,11 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
       }
     }
     __syncwarp();
+  }
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: the t rows of every item
     uint32_t ld = 0, ord = 0;
     int j = pair / sc.groups;
     int item = sched_produce(sc, leader_cta, lane, j, ord++);

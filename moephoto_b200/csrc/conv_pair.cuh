@@ -170,15 +170,19 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   ptx::cluster_sync_all();                        // the peer's barriers are initialised before any remote arrive
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tslot_ptr;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (each CTA loads its own strip)
+  ptx::grid_dep_launch();
+  if (warp == 0) {                                 // the weights are nobody's output: fetched before the dependency wait
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, kChunkImgBytes);
       const uint8_t* src = p.w_img + static_cast<size_t>(my_chunk) * kChunkImgBytes;
       for (int tap = 0; tap < 9; ++tap) ptx::bulk_load_1d(wsm + tap * 8192, src + tap * 8192, 8192, wbar);
     }
     __syncwarp();
+  }
+  ptx::grid_dep_wait();                            // the previous kernel on the stream has finished writing our input
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (each CTA loads its own strip)
     uint32_t ld = 0, ord = 0;
     int j = pair / sc.groups;
     int item = sched_produce(sc, leader_cta, lane, j, ord++);
@@ -423,15 +427,19 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tslot_ptr;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+  ptx::grid_dep_launch();
+  if (warp == 0) {                                 // weights before the dependency wait (see conv3x3_pair_kernel)
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, Cfg::kWBytes);
       for (int tap = 0; tap < 9; ++tap)      // output channels 32*rank .. +31 of every tap
         ptx::bulk_load_1d(wsm + tap * 4096, p.w_img + static_cast<size_t>(chunk) * kChunkImgBytes + tap * 8192 + rank * 4096, 4096, wbar);
     }
     __syncwarp();
+  }
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
     uint32_t ld = 0, ord = 0;
     int j = pair / sc.groups;
     int item = sched_produce(sc, leader_cta, lane, j, ord++);

@@ -95,9 +95,8 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tslot_ptr;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+  ptx::grid_dep_launch();
+  if (warp == 0) {                                 // weights before the dependency wait (see conv3x3_pair_kernel)
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, kChunkImgBytes + 1024);
       const uint8_t* src = p.w_img + static_cast<size_t>(my_chunk) * kChunkImgBytes;
@@ -105,6 +104,11 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
       ptx::bulk_load_1d(hsm, hp.head_img + rank * 1024, 1024, wbar);       // taps 8*rank .. 8*rank+7
     }
     __syncwarp();
+  }
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
     uint32_t ld = 0, ord = 0;
     int j = pair / sc.groups;
     int item = sched_produce(sc, leader_cta, lane, j, ord++);

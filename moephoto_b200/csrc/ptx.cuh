@@ -63,6 +63,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor on the stream is
+// still running: everything before grid_dep_wait() (barrier init, TMEM allocation, weight loads — nothing the predecessor
+// writes) overlaps the predecessor's tail; grid_dep_wait() returns once the predecessor has completed and its writes are
+// visible.  grid_dep_launch() is this grid's permission for ITS successor to do the same.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
