@@ -22,7 +22,7 @@
  * stays on the host: the caller passes it in as a MoePlan.
  *
  * Conventions: plain pointers and sizes only; every function returns MOE_OK (0) or a negative
- * MoeStatus and never aborts the process; moe_last_error() gives the message for the calling thread's
+ * MoeStatus and never aborts the process (not even on a device-side pipeline time-out: moe_engine_check); moe_last_error() gives the message for the calling thread's
  * last failure.  All device pointers are on the engine's device.  `stream` is a cudaStream_t passed as
  * void* (NULL = legacy default stream); work is enqueued on it and the call does not synchronise.
  * Concurrency: calls on one engine may come from several host threads and several streams.  Every convolution launch draws
@@ -114,6 +114,14 @@ int moe_engine_profile_read(MoeEngine* e, double ms[MOE_PROFILE_CLASSES], double
  *        the same half model computes on the CPU (oneDNN adds the bias inside the convolution; tests/golden `.ref16`);
  * bit 6: 1 = run every residual block (ARSB) as two convolution launches instead of the fused arsb_pair_kernel */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
+/* Kernels wait on mbarriers with a time-out (4 s of wall time).  A wait that gives up does NOT trap — round 1's __trap() destroyed
+ * the CUDA context of the whole host process, i.e. MoePhoto's worker and every cached model, and a slow wait (a time-sliced or
+ * profiled GPU) is not an error at all — it raises a device-side flag and the kernel runs on to its end; what it computes after that
+ * is invalid.  moe_engine_check synchronises `stream` and, if the flag is up, clears it, resets the work-item counters and returns
+ * MOE_ERR_CUDA.  moe_enhance_host* / moe_run_band_to_host call it themselves; after moe_run_plan (asynchronous) it is the caller's to
+ * call where it synchronises anyway.  moe_engine_debug_timeout sets the time-out in ns (0 = the default). */
+int moe_engine_check(MoeEngine* e, void* stream);
+int moe_engine_debug_timeout(MoeEngine* e, uint64_t ns);
 /* Diagnostics: `dev` = device buffer of >= 4 * 8 bytes per SM pair (or NULL to switch off).  Every CTA-pair convolution
  * launch then leaves {start ns, end ns, SM id, items processed} per pair in it (the last launch wins). */
 int moe_engine_debug_buffer(MoeEngine* e, void* dev, size_t nbytes);

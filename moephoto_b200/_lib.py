@@ -44,6 +44,8 @@ SYMBOLS = {
   'moe_engine_profile_read': (_i, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
   'moe_engine_set_conv_path': (_i, [_vp, _i]),
   'moe_engine_debug_buffer': (_i, [_vp, _vp, _sz]),
+  'moe_engine_check': (_i, [_vp, _vp]),
+  'moe_engine_debug_timeout': (_i, [_vp, ctypes.c_uint64]),
   'moe_model_load': (_i, [_vp, _i, _vp, _sz, _pp]),
   'moe_model_free': (None, [_vp]),
   'moe_model_scale': (_i, [_vp]),
@@ -87,7 +89,12 @@ def load():
                        '(there is no CPU fallback)' % LIB_PATH)
   lib = ctypes.CDLL(LIB_PATH)
   for name, (res, args) in SYMBOLS.items():
-    fn = getattr(lib, name)   # AttributeError here = the .so does not export what the header declares
+    try:
+      fn = getattr(lib, name)   # AttributeError here = the .so does not export what the header declares
+    except AttributeError:
+      if os.environ.get('MOE_B200_LIB'):
+        continue                # an older build loaded for A/B timing (tools/ab_bench.sh)
+      raise
     fn.restype, fn.argtypes = res, args
   if lib.moe_abi_version() != 1:
     raise RuntimeError('moephoto_b200: ABI version mismatch')

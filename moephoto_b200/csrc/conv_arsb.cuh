@@ -249,7 +249,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
       }
       if (ptx::elect_one()) ptx::mma_commit_pair(dbar);
       __syncwarp();
-      ptx::mbar_wait(dbar, 0);
+      ptx::mbar_wait_drain(dbar, 0);
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------ mid epilogue (warps 2..5): conv_1 accumulator -> fp16 mid row in smem

@@ -77,7 +77,7 @@ __device__ __forceinline__ void sched_publish(const PairSched& s, uint32_t ord, 
 }
 __device__ __forceinline__ int sched_take(const PairSched& s, uint32_t ord) {                 // any warp of either CTA, all lanes
   const uint32_t q = ord % kSchedQ;
-  ptx::mbar_wait_cluster(s.bars + 8 * q, (ord / kSchedQ) & 1);
+  if (!ptx::mbar_wait_cluster(s.bars + 8 * q, (ord / kSchedQ) & 1)) return -1;     // aborted (ptx.cuh): end of the stream for this warp
   return static_cast<int>(ptx::ld_shared_u32(s.items + 4 * q));
 }
 // producer warps of both CTAs, converged: item number `ord` of this pair (ord 0 = the pair's first item, j = pair / groups)
@@ -263,7 +263,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
       }
       if (ptx::elect_one()) ptx::mma_commit_pair(dbar);     // drain
       __syncwarp();
-      ptx::mbar_wait(dbar, 0);
+      ptx::mbar_wait_drain(dbar, 0);
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
@@ -518,7 +518,7 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
       }
       if (ptx::elect_one()) ptx::mma_commit_pair(dbar);
       __syncwarp();
-      ptx::mbar_wait(dbar, 0);
+      ptx::mbar_wait_drain(dbar, 0);
     }
   } else {
     // ------------------------------------------------------------ epilogue (as conv_tc.cuh; tempty lives in the leader)

@@ -276,7 +276,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
       }
       if (ptx::elect_one()) ptx::mma_commit_pair(dbar);     // drain (both MMA streams complete in issue order per thread; see below)
       __syncwarp();
-      ptx::mbar_wait(dbar, 0);
+      ptx::mbar_wait_drain(dbar, 0);
     }
   } else {
     // ------------------------------------------------------------ P readers (warps 11..14): TMEM -> horizontal stencil third -> HBM

@@ -234,7 +234,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     // drain: commits complete in order, so once this one lands no arrive is still in flight
     if (ptx::elect_one()) ptx::mma_commit(wbar);
     __syncwarp();
-    ptx::mbar_wait(wbar, 1);
+    ptx::mbar_wait_drain(wbar, 1);
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int lgrp = warp & 3;                       // TMEM lanes this warp may read: 32*lgrp .. +31

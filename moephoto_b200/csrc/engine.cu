@@ -587,6 +587,30 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   return MOE_OK;
 }
 
+int moe_engine_check(MoeEngine* e, void* stream)
+{
+  if (!e) return fail(MOE_ERR_INVALID, "engine is null");
+  Guard g(e->device);
+  MOE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  unsigned int flag = 0;
+  MOE_CUDA(cudaMemcpyFromSymbol(&flag, ptx::g_mbar_abort, sizeof flag));
+  if (!flag) return MOE_OK;
+  flag = 0;
+  MOE_CUDA(cudaMemcpyToSymbol(ptx::g_mbar_abort, &flag, sizeof flag));
+  // the work-item counters of the aborted launches were left mid-count: start every block from zero again
+  MOE_CUDA(cudaMemset(e->d_sched, 0, kSchedRing * kSchedStride * sizeof(int)));
+  return fail(MOE_ERR_CUDA, "a kernel gave up waiting on an mbarrier (pipeline protocol error or a stalled GPU): the results since the last check are invalid; the engine remains usable");
+}
+
+int moe_engine_debug_timeout(MoeEngine* e, uint64_t ns)
+{
+  if (!e) return fail(MOE_ERR_INVALID, "engine is null");
+  Guard g(e->device);
+  unsigned long long v = ns ? ns : 4000000000ull;
+  MOE_CUDA(cudaMemcpyToSymbol(ptx::g_mbar_timeout_ns, &v, sizeof v));
+  return MOE_OK;
+}
+
 int moe_engine_debug_buffer(MoeEngine* e, void* dev, size_t nbytes)
 {
   if (!e) return fail(MOE_ERR_INVALID, "engine is null");
@@ -608,15 +632,24 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
   if (h.n_up > 3 || (h.n_up && h.r != 2 && h.r != 3) || (h.n_up >= 2 && h.r != 2)) return fail(MOE_ERR_INVALID, "unsupported upsample layout");
   if (arch != MOE_ARCH_NET2X && arch != MOE_ARCH_NET3X && arch != MOE_ARCH_NET4X && arch != MOE_ARCH_NETDN && arch != MOE_ARCH_LITE)
     return fail(MOE_ERR_INVALID, "unknown architecture %d", arch);
-  if (nbytes < sizeof h + h.n_sections * sizeof(BlobEntry)) return fail(MOE_ERR_INVALID, "truncated directory");
+  if (h.n_sections > 256 || nbytes < sizeof h + h.n_sections * sizeof(BlobEntry)) return fail(MOE_ERR_INVALID, "truncated directory");
+  {
+    // the header must describe the architecture it names (the table of moephoto_b200/weights.py::pack)
+    static const struct { int arch; uint32_t feat, n_up, r; } kLayouts[] = {
+      {MOE_ARCH_NETDN, 48, 0, 0}, {MOE_ARCH_NET2X, 64, 1, 2}, {MOE_ARCH_NET3X, 64, 1, 3}, {MOE_ARCH_NET4X, 64, 2, 2}};
+    bool known = arch == MOE_ARCH_LITE && h.feat == 48 && h.r == 2 && h.n_up >= 1 && h.n_up <= 3;
+    for (const auto& l : kLayouts) known = known || (l.arch == arch && l.feat == h.feat && l.n_up == h.n_up && l.r == h.r);
+    if (!known) return fail(MOE_ERR_INVALID, "header (feat %u, n_up %u, r %u) does not describe architecture %d", h.feat, h.n_up, h.r, arch);
+  }
   Guard g(e->device);
   if (!g.ok) return fail(MOE_ERR_CUDA, "cudaSetDevice failed");
   MoeModel* m = new MoeModel();
   m->e = e; m->arch = arch; m->feat = h.feat; m->n_up = h.n_up; m->r = h.r;
   m->scale = 1;
   for (uint32_t i = 0; i < h.n_up; ++i) m->scale *= static_cast<int>(h.r);
-  if (cudaMalloc(&m->d_blob, nbytes) != cudaSuccess) { delete m; cudaGetLastError(); return fail(MOE_ERR_NOMEM, "cudaMalloc(%zu) for weights failed", nbytes); }
-  if (cudaMemcpy(m->d_blob, blob, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_CUDA, "weight upload failed"); }
+  // every failure exit below goes through moe_model_free: nothing allocated so far is leaked
+  if (cudaMalloc(&m->d_blob, nbytes) != cudaSuccess) { cudaGetLastError(); moe_model_free(m); return fail(MOE_ERR_NOMEM, "cudaMalloc(%zu) for weights failed", nbytes); }
+  if (cudaMemcpy(m->d_blob, blob, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); moe_model_free(m); return fail(MOE_ERR_CUDA, "weight upload failed"); }
   const uint8_t* hb = static_cast<const uint8_t*>(blob);
   bool have_scalars = false;
   int n_trunk = 0, n_head = 0, n_up_img = 0, n_up_bias = 0, n_frm = 0;
@@ -624,7 +657,7 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
   for (uint32_t i = 0; i < h.n_sections; ++i) {
     BlobEntry en;
     memcpy(&en, hb + sizeof h + i * sizeof en, sizeof en);
-    bool bad = en.offset % 256 || en.offset + en.nbytes > nbytes;
+    bool bad = en.offset % 256 || en.nbytes > nbytes || en.offset > nbytes - en.nbytes;       // no wrap-around for a crafted blob
     const uint8_t* dp = m->d_blob + en.offset;
     switch (en.kind) {
       case SEC_FIRST_W: bad |= en.nbytes != 9 * 64 * 4; m->first_w = reinterpret_cast<const float*>(dp); break;
@@ -636,7 +669,7 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
       case SEC_HEAD_W: bad |= en.index >= 2 || en.nbytes != 9 * 64 * 4; if (!bad) { m->head_w[en.index] = reinterpret_cast<const float*>(dp); ++n_head; } break;
       default: bad = true;
     }
-    if (bad) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "bad blob section %u (kind %u index %u)", i, en.kind, en.index); }
+    if (bad) { moe_model_free(m); return fail(MOE_ERR_INVALID, "bad blob section %u (kind %u index %u)", i, en.kind, en.index); }
   }
   const int want_up = 2 * static_cast<int>(h.n_up);
   const bool lite = arch == MOE_ARCH_LITE;
@@ -645,7 +678,7 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
   for (int l = 0; l < (lite ? 7 : 13) && complete; ++l) complete = m->trunk_img[l] != nullptr;
   for (int b = 0; b < 2 && complete; ++b)
     for (uint32_t s = 0; s < h.n_up && complete; ++s) complete = m->up_img[4 * b + s] && m->up_bias[4 * b + s];
-  if (!complete) { cudaFree(m->d_blob); delete m; return fail(MOE_ERR_INVALID, "blob is missing sections"); }
+  if (!complete) { moe_model_free(m); return fail(MOE_ERR_INVALID, "blob is missing sections"); }
   {
     // head filters as a K-major SWIZZLE_128B B operand: row = tap (9 of 16 used), 64 input channels
     std::vector<__half> img(2 * 16 * 64, __float2half(0.f));
@@ -657,7 +690,7 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
     }
     if (cudaMalloc(&m->d_head_img, 4096) != cudaSuccess ||
         cudaMemcpy(m->d_head_img, img.data(), 4096, cudaMemcpyHostToDevice) != cudaSuccess) {
-      cudaGetLastError(); cudaFree(m->d_blob); delete m;
+      cudaGetLastError(); moe_model_free(m);
       return fail(MOE_ERR_NOMEM, "head weight upload failed");
     }
   }
@@ -753,9 +786,9 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     fp.top = t.top + g.c0; fp.left = t.left; fp.N = N; fp.H = H; fp.W = W;
     fp.w = m->first_w; fp.slope = m->scalars[0]; fp.out = bufA;
     e->cur_feat = m->feat;
+    if (N > 65535) return fail(MOE_ERR_INVALID, "too many planes for the conv_input grid");
     {
     Timed timed(e, st, 0, static_cast<double>(N) * H * W * (2 + 128));     // bytes: read 1 fp16, write 64 fp16
-    if (N > 65535) return fail(MOE_ERR_INVALID, "too many planes for the conv_input grid");
     int first_rows = 0, first_nseg = 0;
     choose_segments(static_cast<int64_t>(N) * ((W + 127) / 128), 2 * e->sm_count, H, 8, &first_rows, &first_nseg);
     conv_first_kernel<<<dim3((W + 127) / 128, first_nseg, N), 256, 0, st>>>(fp, first_rows);
@@ -1037,8 +1070,7 @@ int moe_enhance_host_c(MoeModel* m, const void* host_in, int bits_in, int channe
                           plan, 0, plan->out_h, e->buf[4], e->cap[4], st, one_row ? overlap_after_tile : nullptr, &ctx)) != MOE_OK) return rc;
   if ((rc = flush_columns(&ctx, plan->out_w)) != MOE_OK) return rc;
   MOE_CUDA(cudaStreamSynchronize(e->copy_stream));
-  MOE_CUDA(cudaStreamSynchronize(st));
-  return MOE_OK;
+  return moe_engine_check(e, stream);
 }
 
 int moe_enhance_host(MoeModel* m, const void* host_in, int bits_in, const MoePlan* plan, void* host_out, int bits_out, void* stream)
@@ -1076,8 +1108,7 @@ int moe_run_band_to_host(MoeModel* m, const void* in, int64_t in_plane_stride, i
                           e->buf[4], e->cap[4], st, one_row ? overlap_after_tile : nullptr, &ctx)) != MOE_OK) return rc;
   if ((rc = flush_columns(&ctx, plan->out_w)) != MOE_OK) return rc;
   MOE_CUDA(cudaStreamSynchronize(e->copy_stream));
-  MOE_CUDA(cudaStreamSynchronize(st));
-  return MOE_OK;
+  return moe_engine_check(e, stream);
 }
 
 }  // extern "C"

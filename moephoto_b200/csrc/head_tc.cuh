@@ -133,7 +133,7 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadTcParams p)
     }
     if (ptx::elect_one()) ptx::mma_commit(wbar);
     __syncwarp();
-    ptx::mbar_wait(wbar, 1);
+    ptx::mbar_wait_drain(wbar, 1);
   } else {
     const int lgrp = warp & 3;
     const int L = lgrp * 32 + lane;                 // loaded pixel index 0..127

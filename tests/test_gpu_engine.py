@@ -13,6 +13,7 @@ Tolerances, all stated here:
   * integer frame conversions, band sharding, determinism: bit-exact.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -323,6 +324,19 @@ def test_errors_are_status_codes_not_crashes(engine):
     cfgopt = _sr_opt('a2', 2, ram=1000)
     IP.doCrop(cfgopt, x)
   config.freeMemOverride = None
+  # crafted blobs: a header that does not describe its architecture, a section whose offset + size wraps around
+  import struct
+  from moephoto_b200 import weights as W
+  arch, blob = W.pack(H.load_weights('a2'))
+  load = lambda bts: engine.lib.moe_model_load(engine.handle, arch, (ctypes.c_uint8 * len(bts)).from_buffer_copy(bts), len(bts), ctypes.byref(h))
+  lied = bytearray(blob)
+  struct.pack_into('<I', lied, 16, 3)                                        # n_up = 3 in a Net2x blob
+  assert load(bytes(lied)) == _lib.MOE_ERR_INVALID
+  wrap = bytearray(blob)
+  struct.pack_into('<Q', wrap, 32 + 8, 2 ** 64 - 256)                        # first section: offset just below 2^64
+  assert load(bytes(wrap)) == _lib.MOE_ERR_INVALID and b'bad blob section' in engine.lib.moe_last_error()
+  assert load(blob) == _lib.MOE_OK                                           # the engine is unharmed
+  engine.lib.moe_model_free(h)
 
 
 def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
@@ -656,3 +670,21 @@ def test_video_pipe_loop_equals_the_reference_frame_loop(engine):
         assert video.pipe_loop(io.BytesIO(b'').read, pipe_out.write, h, w, [odn, osr]) == 0
     finally:
         config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
+
+
+def test_engine_check_reports_no_timeout_in_normal_operation(engine):
+    """the kernels' mbarrier waits give up after a time-out by raising a device flag (no __trap: DESIGN.md §5, include/moephoto_b200.h);
+    moe_engine_check is how the host sees it.  In normal operation, even with the time-out shrunk to 50 ms, it never fires."""
+    from moephoto_b200 import _lib, imageProcess as IP
+    from moephoto_b200.config import config
+    opt = _sr_opt('a4', 4, crop=96)
+    try:
+        x = torch.rand(3, 200, 300, generator=torch.Generator().manual_seed(1)).half().cuda()
+        want = IP.doCrop(opt, x).clone()
+        _lib.check(engine.lib.moe_engine_debug_timeout(engine.handle, 50000000))
+        got = IP.doCrop(opt, x)
+        assert engine.lib.moe_engine_check(engine.handle, None) == _lib.MOE_OK
+        assert torch.equal(got, want)
+    finally:
+        engine.lib.moe_engine_debug_timeout(engine.handle, 0)
+        config.freeMemOverride = None
