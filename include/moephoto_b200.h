@@ -112,7 +112,8 @@ int moe_engine_profile_read(MoeEngine* e, double ms[MOE_PROFILE_CLASSES], double
  * bit 5: numerics of a convolution WITH a bias (models.py:29-30): 0 (default) = q(q(conv) + bias), what the reference's GPU
  *        path computes (aten: cudnn_convolution, then add_ of the bias — two ops, two fp16 roundings), 1 = q(conv + bias), what
  *        the same half model computes on the CPU (oneDNN adds the bias inside the convolution; tests/golden `.ref16`);
- * bit 6: 1 = run every residual block (ARSB) as two convolution launches instead of the fused arsb_pair_kernel */
+ * bit 6: 1 = run every residual block (ARSB) as two convolution launches instead of the fused arsb_pair_kernel;
+ * bit 7: 1 = the fused residual block keeps its intermediate rows in shared memory (.ss conv_2) instead of tensor memory (.ts) */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
 /* Kernels wait on mbarriers with a time-out (4 s of wall time).  A wait that gives up does NOT trap — round 1's __trap() destroyed
  * the CUDA context of the whole host process, i.e. MoePhoto's worker and every cached model, and a slow wait (a time-sliced or

@@ -41,15 +41,27 @@ struct ArsbMaps {
 
 constexpr int kArsbStripW = 126;
 
-struct ArsbCfg {
-  static constexpr int kTSlots = 5;
-  static constexpr int kMSlots = 3;
-  static constexpr int kAcc = 4;                                  // accumulator stages per convolution
-  static constexpr uint32_t kMSlotBytes = 16384;                  // 128 mid pixels; the scrap outputs read 2 rows past it
+// kMidTmem = false: `mid` rows live in a shared-memory ring and conv_2 is an .ss MMA like conv_1 (round 2, first form).
+// kMidTmem = true : `mid` rows live in TENSOR memory and conv_2 is a .ts MMA — its A operand costs no shared-memory bandwidth.
+//   TMEM lanes cannot be shifted, so the mid epilogue writes every row three times (the dx = 0, 1, 2 views: lane j holds mid
+//   position j + dx; the neighbours' pixels arrive by warp shuffle, across warps through 2 KB of shared memory) with tcgen05.st:
+//   4 rows x 3 views x 32 columns = 384 TMEM columns, which leaves one 64-column accumulator per convolution.  One stage each is
+//   enough because the two convolutions alternate in the tensor pipe: an accumulator is drained while the OTHER convolution runs.
+template <bool kMidTmem>
+struct ArsbCfgT {
+  static constexpr int kTSlots = kMidTmem ? 6 : 5;
+  static constexpr int kMSlots = kMidTmem ? 4 : 3;
+  static constexpr int kAcc = kMidTmem ? 1 : 4;                   // accumulator stages per convolution
+  static constexpr uint32_t kMSlotBytes = 16384;                  // (smem form) 128 mid pixels; the scrap outputs read 2 rows past it
+  static constexpr uint32_t kMidCols = 96;                        // (TMEM form) columns of one mid row: 3 views x 64 fp16
+  static constexpr uint32_t kAcc1Col = kMidTmem ? 4 * kMidCols : 0;
+  static constexpr uint32_t kAcc2Col = kMidTmem ? 4 * kMidCols + 64 : 4 * 64;
   static constexpr uint32_t kWBytes = 9 * 32 * 128;               // one convolution, this CTA's half of the output channels
-  static constexpr uint32_t kTmemCols = 2 * kAcc * 64;            // 512
-  static constexpr uint32_t kSmemBytes = 1024 + kTSlots * kSlotBytes + kMSlots * kMSlotBytes + 2 * kWBytes + kStageBytes + 1024;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t kMidBytes = kMidTmem ? 2048 : kMSlots * kMSlotBytes;    // TMEM form: the cross-warp exchange of the mid epilogue
+  static constexpr uint32_t kSmemBytes = 1024 + kTSlots * kSlotBytes + kMidBytes + 2 * kWBytes + kStageBytes + 1024;
 };
+using ArsbCfg = ArsbCfgT<false>;
 
 // rows of one item: outputs [y0, y1), mid rows [m_lo, m_hi] (the ones inside the tile), t rows [y0 - 2, y1 + 1]
 struct ArsbItem { int n, sp, y0, y1, m_lo, m_hi; };
@@ -61,10 +73,11 @@ __device__ __forceinline__ ArsbItem arsb_decode(const ConvParams& p, int item) {
   return it;
 }
 
+template <bool kMidTmem>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 {
-  using Cfg = ArsbCfg;
+  using Cfg = ArsbCfgT<kMidTmem>;
   constexpr int TS = Cfg::kTSlots, MS = Cfg::kMSlots, AS = Cfg::kAcc;
   const ConvParams& p = ap.c;
   extern __shared__ uint8_t smem_raw[];
@@ -73,7 +86,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t tring = base;
   const uint32_t mring = tring + TS * kSlotBytes;
-  const uint32_t w1sm = mring + MS * Cfg::kMSlotBytes;
+  const uint32_t w1sm = mring + Cfg::kMidBytes;
   const uint32_t w2sm = w1sm + Cfg::kWBytes;
   const uint32_t stg = w2sm + Cfg::kWBytes;
   const uint32_t bars = stg + kStageBytes;
@@ -98,7 +111,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 
   if (tid == 0) {
     for (int i = 0; i < TS; ++i) { ptx::mbar_init(tfull_t + 8 * i, 1); ptx::mbar_init(tempty_t + 8 * i, 4); }
-    for (int i = 0; i < MS; ++i) { ptx::mbar_init(mfull + 8 * i, 2); ptx::mbar_init(mempty + 8 * i, 1); }
+    for (int i = 0; i < MS; ++i) { ptx::mbar_init(mfull + 8 * i, kMidTmem ? 2 * 4 : 2); ptx::mbar_init(mempty + 8 * i, 1); }
     for (int i = 0; i < AS; ++i) {
       ptx::mbar_init(a1full + 8 * i, 1); ptx::mbar_init(a1empty + 8 * i, 2 * 4);
       ptx::mbar_init(a2full + 8 * i, 1); ptx::mbar_init(a2empty + 8 * i, 2 * 4);
@@ -179,7 +192,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
           const uint32_t stage = n1 % AS;
           ptx::mbar_wait(a1empty + 8 * stage, ((n1 / AS) & 1) ^ 1);
           ptx::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + stage * 64;
+          const uint32_t d_tmem = tmem_base + Cfg::kAcc1Col + stage * 64;
           const uint64_t r0 = at0 + static_cast<uint64_t>((e0 % TS) * (kSlotBytes >> 4));
           const uint64_t r1 = at0 + static_cast<uint64_t>(((e0 + 1) % TS) * (kSlotBytes >> 4));
           const uint64_t r2 = at0 + static_cast<uint64_t>(((e0 + 2) % TS) * (kSlotBytes >> 4));
@@ -201,7 +214,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
         for (int y = it.y0; y < it.y1; ++y) {
           // conv_1 runs two mid rows ahead of conv_2 — except before the item's first output row: C1(y0+2) needs t row y0+3, the
           // SIXTH row of the item, and the 5-slot ring only turns over once the output epilogue of row y0 has released its slots
-          const int want = min(y == it.y0 ? y + 1 : y + 2, it.m_hi);
+          const int want = min((y == it.y0 && TS < 6) ? y + 1 : y + 2, it.m_hi);
           while (next_m <= want) conv1(next_m++);
           if (y == it.y1 - 1) {
             // the output epilogue releases the item's last t slots after THIS conv_2: every load of the item must have landed
@@ -213,12 +226,13 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
           const int lo = max(y - 1, it.m_lo), hi = min(y + 1, it.m_hi);
           for (int m = lo; m <= hi; ++m) {
             const uint32_t e = mcnt + static_cast<uint32_t>(m - it.m_lo);
-            ptx::mbar_wait_cluster(mfull + 8 * (e % MS), (e / MS) & 1);       // written by both CTAs' mid epilogues
+            if (kMidTmem) ptx::mbar_wait(mfull + 8 * (e % MS), (e / MS) & 1);  // TMEM rows: ordered by the tcgen05 fences
+            else ptx::mbar_wait_cluster(mfull + 8 * (e % MS), (e / MS) & 1);   // smem rows written by both CTAs' mid epilogues
           }
           const uint32_t stage = n2 % AS;
           ptx::mbar_wait(a2empty + 8 * stage, ((n2 / AS) & 1) ^ 1);
           ptx::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + AS * 64 + stage * 64;
+          const uint32_t d_tmem = tmem_base + Cfg::kAcc2Col + stage * 64;
           if (ptx::elect_one()) {
             bool first = true;
 #pragma unroll
@@ -227,11 +241,13 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
               if (m < it.m_lo || m > it.m_hi) continue;                       // zero padding above / below the tile
               const uint32_t e = mcnt + static_cast<uint32_t>(m - it.m_lo);
               const uint64_t arow = am0 + static_cast<uint64_t>((e % MS) * (Cfg::kMSlotBytes >> 4));
+              const uint32_t trow = tmem_base + (e % MS) * Cfg::kMidCols;
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), b2 + ((dy * 3 + dx) * 256 + k * 2), idesc, first ? 0u : 1u);
+                  if (kMidTmem) ptx::mma_f16_ts_pair(d_tmem, trow + dx * 32 + k * 8, b2 + ((dy * 3 + dx) * 256 + k * 2), idesc, first ? 0u : 1u);
+                  else ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), b2 + ((dy * 3 + dx) * 256 + k * 2), idesc, first ? 0u : 1u);
                   first = false;
                 }
             }
@@ -272,7 +288,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
-          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + stage * 64 + h * 32, v);
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + Cfg::kAcc1Col + stage * 64 + h * 32, v);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -292,15 +308,49 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(a1empty_leader + 8 * stage);   // accumulator stage back to the MMA warp
         const uint32_t ms = mc % MS;
-        ptx::mbar_wait(mempty + 8 * ms, ((mc / MS) & 1) ^ 1);                  // conv_2 has finished with this slot's previous row
-        uint8_t* row = mring_ptr + ms * Cfg::kMSlotBytes + L * 128;
+        if (!kMidTmem) {
+          ptx::mbar_wait(mempty + 8 * ms, ((mc / MS) & 1) ^ 1);                // conv_2 has finished with this slot's previous row
+          uint8_t* row = mring_ptr + ms * Cfg::kMSlotBytes + L * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = pk[c];
-        ptx::fence_proxy_async_smem();                                         // generic-proxy writes -> the tensor core's async proxy
-        ptx::named_bar_sync(1, 128);
-        if (warp == 2) {
-          if (ptx::elect_one()) ptx::mbar_arrive_cluster_release(mfull_leader + 8 * ms);
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = pk[c];
+          ptx::fence_proxy_async_smem();                                       // generic-proxy writes -> the tensor core's async proxy
+          ptx::named_bar_sync(1, 128);
+          if (warp == 2) {
+            if (ptx::elect_one()) ptx::mbar_arrive_cluster_release(mfull_leader + 8 * ms);
+            __syncwarp();
+          }
+        } else {
+          // view dx of the row: THIS lane must hold mid position L + dx.  Positions L+1, L+2 sit in the next lanes; the last two
+          // lanes of a warp take them from the first two lanes of the next warp through shared memory (positions >= 128 feed
+          // only the two scrap outputs: zeros).  xbuf[row parity][warp][lane 0 / 1][32 words]
+          uint32_t* xb = reinterpret_cast<uint32_t*>(mring_ptr) + (mc & 1) * 256;
+          if (lane < 2) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(xb + (lgrp * 2 + lane) * 32 + c * 4) = pk[c];
+          }
+          ptx::named_bar_sync(1, 128);
+          ptx::mbar_wait(mempty + 8 * ms, ((mc / MS) & 1) ^ 1);                // conv_2 has finished with this TMEM row's previous tenant
+          ptx::tc_fence_after_sync();
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + ms * Cfg::kMidCols;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            uint32_t v[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t o[4] = {pk[c].x, pk[c].y, pk[c].z, pk[c].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                uint32_t w = dx == 0 ? o[e] : __shfl_down_sync(0xffffffffu, o[e], dx);
+                if (dx > 0 && lane + dx >= 32) w = lgrp < 3 ? xb[((lgrp + 1) * 2 + (lane + dx - 32)) * 32 + c * 4 + e] : 0u;
+                v[c * 4 + e] = w;
+              }
+            }
+            ptx::tmem_st32(trow + dx * 32, v);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
           __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(mfull_leader + 8 * ms);      // count 2 x 4 warps
         }
       }
     }
@@ -338,7 +388,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
-          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + AS * 64 + stage * 64 + h * 32, v);
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + Cfg::kAcc2Col + stage * 64 + h * 32, v);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

@@ -67,6 +67,7 @@ struct MoeEngine {
   int no_pair = 0;         // 1 = keep every conv on the single-CTA kernel (A/B switch)
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
   int no_fuse = 0;         // 1 = last upsample conv and heads stay separate kernels (conv3x3_pair_kernel + head_tc_kernel)
+  int arsb_smem_mid = 0;   // 1 = the fused residual block keeps its mid rows in shared memory (.ss conv_2) instead of TMEM (.ts)
   int no_arsb = 0;         // 1 = every residual block as two launches of the trunk kernel instead of arsb_pair_kernel (A/B switch)
   bool arsb_attr_set = false;
   int bias_fused = 0;      // 1 = biased convolutions round once, q(conv + bias): the half model executed on the CPU (goldens); 0 = the GPU's two ops
@@ -333,11 +334,15 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the residual block", (int)cr);
   if (!e->arsb_attr_set) {
-    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfg::kSmemBytes));
+    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<false>::kSmemBytes));
+    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<true>::kSmemBytes));
     e->arsb_attr_set = true;
   }
   const int npairs = static_cast<int>(std::min<int64_t>(npairs_max, p.items));
-  MOE_CUDA(launch_pdl(arsb_pair_kernel, 2 * npairs, kConvThreads, ArsbCfg::kSmemBytes, st, maps, ap));
+  if (e->arsb_smem_mid)
+    MOE_CUDA(launch_pdl(arsb_pair_kernel<false>, 2 * npairs, kConvThreads, ArsbCfgT<false>::kSmemBytes, st, maps, ap));
+  else
+    MOE_CUDA(launch_pdl(arsb_pair_kernel<true>, 2 * npairs, kConvThreads, ArsbCfgT<true>::kSmemBytes, st, maps, ap));
   return check_launch(e, "arsb_pair_kernel");
 }
 
@@ -584,6 +589,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   e->static_sched = (simt >> 4) & 1;
   e->bias_fused = (simt >> 5) & 1;
   e->no_arsb = (simt >> 6) & 1;
+  e->arsb_smem_mid = (simt >> 7) & 1;
   return MOE_OK;
 }
 
