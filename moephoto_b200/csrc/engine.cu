@@ -20,6 +20,7 @@
 #include "conv_pair.cuh"
 #include "conv_pair_head.cuh"
 #include "conv_arsb.cuh"
+#include "conv_arsb_solo.cuh"
 #include "kernels_simt.cuh"
 #include "head_tc.cuh"
 
@@ -68,8 +69,10 @@ struct MoeEngine {
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
   int no_fuse = 0;         // 1 = last upsample conv and heads stay separate kernels (conv3x3_pair_kernel + head_tc_kernel)
   int arsb_smem_mid = 0;   // 1 = the fused residual block keeps its mid rows in shared memory (.ss conv_2) instead of TMEM (.ts)
+  int arsb_solo = 0;       // 1 = the fused residual block on single CTAs with full weights per SM (conv_arsb_solo.cuh) instead of CTA pairs
   int no_arsb = 0;         // 1 = every residual block as two launches of the trunk kernel instead of arsb_pair_kernel (A/B switch)
   bool arsb_attr_set = false;
+  bool arsb_solo_attr_set = false;
   int bias_fused = 0;      // 1 = biased convolutions round once, q(conv + bias): the half model executed on the CPU (goldens); 0 = the GPU's two ops
   int static_sched = 0;    // 1 = pair kernels deal their items round-robin instead of drawing them (conv_pair.cuh, item scheduler)
   // the item scheduler's counters: a ring of kSchedRing blocks of kSchedInts ints, one block per pair-kernel launch (the
@@ -312,6 +315,33 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg;
   ap.w2_img = w2_img; ap.scale = scale;
   Timed timed(e, st, 4, 2 * 2.0 * 9 * e->cur_feat * static_cast<double>(e->cur_feat) * N * H * W);   // both convolutions
+  if (e->arsb_solo) {
+    if (const char* x = getenv("MOE_ARSB_EXP")) p.center_only = atoi(x);
+    // one CTA per SM, full weights of both convolutions per SM (conv_arsb_solo.cuh)
+    p.strips = (W + kArsbStripW - 1) / kArsbStripW;
+    const int64_t base_items = static_cast<int64_t>(N) * p.strips;
+    choose_segments(base_items, e->sm_count, H, 16, &p.seg_rows, &p.nseg);
+    const int64_t items = base_items * p.nseg;
+    if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
+    p.items = static_cast<int>(items);
+    ArsbMaps maps;
+    memset(&maps, 0, sizeof maps);
+    const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {128, dims[1] * 128, dims[1] * dims[2] * 128};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box_in[4] = {64, kRowPx, 1, 1};
+    const CUresult cr = e->encode(&maps.in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box_in, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the residual block", (int)cr);
+    if (!e->arsb_solo_attr_set) {
+      MOE_CUDA(cudaFuncSetAttribute(arsb_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbSoloCfg::kSmemBytes));
+      e->arsb_solo_attr_set = true;
+    }
+    const int grid = static_cast<int>(std::min<int64_t>(e->sm_count, p.items));
+    MOE_CUDA(launch_pdl(arsb_solo_kernel, grid, kArsbSoloThreads, ArsbSoloCfg::kSmemBytes, st, maps, ap));
+    return check_launch(e, "arsb_solo_kernel");
+  }
   const int npairs_max = e->sm_count / 2;
   const int strips1 = (W + kArsbStripW - 1) / kArsbStripW;
   p.strips = (strips1 + 1) / 2;                                // strip PAIRS of 2 x 126 px
@@ -590,6 +620,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   e->bias_fused = (simt >> 5) & 1;
   e->no_arsb = (simt >> 6) & 1;
   e->arsb_smem_mid = (simt >> 7) & 1;
+  e->arsb_solo = (simt >> 8) & 1;
   return MOE_OK;
 }
 

@@ -377,7 +377,7 @@ def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
     config.freeMemOverride, config.crop_dn, config.crop_sr = None, 'auto', 'auto'
 
 
-@pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True), dict(static_sched=True), dict(no_arsb=True), dict(arsb_smem_mid=True)])
+@pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True), dict(static_sched=True), dict(no_arsb=True), dict(arsb_smem_mid=True), dict(arsb_solo=True)])
 @pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'lite2_tiled', 'lite8_single'])
 def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags):
     """the A/B switches keep the single-CTA conv kernel, the unfused CTA-pair kernel and head_tc_kernel alive;
@@ -392,7 +392,7 @@ def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags
     H.assert_ref16_bar(y, c, ref=H.run_case_oracle(c, mode='ref16'), what='variant vs oracle ref16')
     assert H.psnr(y, c['ref']) >= 60.0
     assert np.abs(y - y_default).max() <= 1e-3
-    if flags.get('static_sched') or flags.get('no_arsb') or flags.get('arsb_smem_mid'):
+    if flags.get('static_sched') or flags.get('no_arsb') or flags.get('arsb_smem_mid') or flags.get('arsb_solo'):
         # who computes an item never changes its result; and the fused residual block has the rounding points AND the MMA
         # accumulation order of its two-launch form
         assert np.array_equal(y, y_default)
@@ -574,7 +574,7 @@ def test_fused_residual_block_is_bit_identical_to_its_two_launch_form(engine, ke
         x = torch.rand(shape, generator=torch.Generator().manual_seed(sum(shape))).half().cuda()
         y = IP.doCrop(opt, x)                                # mid rows in tensor memory, conv_2 a .ts MMA (the default)
         assert torch.isfinite(y).all()
-        for flags in (dict(no_arsb=True), dict(arsb_smem_mid=True)):
+        for flags in (dict(no_arsb=True), dict(arsb_smem_mid=True), dict(arsb_solo=True)):
             engine.set_conv_path(**flags)
             try:
                 y2 = IP.doCrop(opt, x)

@@ -1,5 +1,5 @@
 """One reference tile of the bench workload (a4 on 3 x 2160 x 968, what one of the four column strips of a 4K frame is) for
-ncu captures:  python tools/prof_tile.py [model key] [scale] [h] [w] [runs]"""
+ncu captures:  [MOE_CONV_FLAGS=arsb_solo,...] python tools/prof_tile.py [model key] [scale] [h] [w] [runs]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,6 +20,7 @@ if key.startswith('dn'):
 else:
   opt = runSR.getOpt({'model': 'lite' if key.startswith('lite') else key[0], 'scale': scale}, weights=sd)
   f = runSR.sr(opt)
+IP.getEngine().set_conv_path(**{k: True for k in os.environ.get('MOE_CONV_FLAGS', '').split(',') if k})
 x = torch.rand(3, h, w, generator=torch.Generator().manual_seed(0)).half().cuda()
 for _ in range(runs):
   y = f(x)
