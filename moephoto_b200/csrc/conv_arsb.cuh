@@ -73,7 +73,9 @@ __device__ __forceinline__ ArsbItem arsb_decode(const ConvParams& p, int item) {
   return it;
 }
 
-template <bool kMidTmem>
+// KS: K steps of 16 input channels per tap, 4 or 3 (ConvParams::ksteps) — a template parameter because the one thread that issues
+// every MMA of the CTA pair has no cycle to spare for a predicate (a run-time test made the kernel 1.6x slower)
+template <bool kMidTmem, int KS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 {
@@ -203,7 +205,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < KS; ++k)
                   ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), b1 + ((dy * 3 + dx) * 256 + k * 2), idesc, (dy | dx | k) != 0);
             }
             ptx::mma_commit_pair_mc(a1full + 8 * stage, 3);
@@ -245,7 +247,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < KS; ++k) {
                   if (kMidTmem) ptx::mma_f16_ts_pair(d_tmem, trow + dx * 32 + k * 8, b2 + ((dy * 3 + dx) * 256 + k * 2), idesc, first ? 0u : 1u);
                   else ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), b2 + ((dy * 3 + dx) * 256 + k * 2), idesc, first ? 0u : 1u);
                   first = false;

@@ -45,6 +45,7 @@ __device__ __forceinline__ ArsbItem arsb_solo_decode(const ConvParams& p, int it
   return it;
 }
 
+template <int KS>
 __global__ void __launch_bounds__(kArsbSoloThreads, 1)
 arsb_solo_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 {
@@ -197,7 +198,7 @@ arsb_solo_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < KS; ++k) {
                   ptx::mma_f16_ss(d_tmem, arow + (dx * 8 + k * 2), b1 + ((dy * 3 + dx) * 512 + k * 2), idesc, (dy | dx | k) != 0);
                 }
             }
@@ -244,7 +245,7 @@ arsb_solo_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < KS; ++k) {
                 ptx::mma_f16_ts(d_tmem, trow + dx * 32 + k * 8, b2 + ((dy * 3 + dx) * 512 + k * 2), idesc, first ? 0u : 1u);
                 first = false;
               }

@@ -122,7 +122,7 @@ __device__ __forceinline__ void pair_decode_item(const ConvParams& p, int item, 
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
-conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
+conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p, const __grid_constant__ ConvBias cb)
 {
   using Cfg = PairCfg;
   constexpr int S = Cfg::kSlots, AS = Cfg::kAccStages;
@@ -136,11 +136,9 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
   const uint32_t bars = stg + 2 * kStageBytes;
   const uint32_t full = bars, empty = full + 8 * S, tfull = empty + 8 * S, tempty = tfull + 8 * AS;
   const uint32_t wbar = tempty + 8 * AS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
-  const uint32_t bias_sm = bars + 256;                              // 128 floats, 16-byte aligned for float4 reads
   const uint32_t sq_items = bars + 768, sq_bars = bars + 832;       // item queue (kSchedQ ints + kSchedQ barriers)
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
   uint8_t* stg_ptr = smem + (stg - base);
-  float* bias_ptr = reinterpret_cast<float*>(smem + (bias_sm - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -163,7 +161,6 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&maps.in);
   }
-  for (int i = tid; i < 128; i += kConvThreads) bias_ptr[i] = p.bias[min(g_fixed * 2 + (i >> 6), nchunks - 1) * 64 + (i & 63)];
   if (warp == 1) ptx::tmem_alloc_pair(tslot, Cfg::kTmemCols);
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -243,7 +240,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
               for (int dx = 0; dx < 3; ++dx) {
               if (p.center_only && (dy != 1 || dx != 1)) continue;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 4; ++k) if (k < p.ksteps) {
                   ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, p.center_only ? (k != 0) : ((dy | dx | k) != 0));
                 }
               }
@@ -274,7 +271,7 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
     uint8_t* my_row = stg_ptr + ch * kStageBytes + L * 128;
     const int sw = L & 7;
     const uint32_t tempty_leader = ptx::mapa(tempty, 0);
-    const float* my_bias = bias_ptr + ch * 64;
+    const int my_bias = min(g_fixed * 2 + ch, nchunks - 1) * 64;        // index into cb.v (constant bank)
     const CUtensorMap* omap0 = &maps.out[g_fixed * 2];
     const CUtensorMap* omap1 = &maps.out[min(g_fixed * 2 + 1, nchunks - 1)];
     const bool two_chunks = g_fixed * 2 + 1 < nchunks;
@@ -296,15 +293,12 @@ conv3x3_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 b0 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = q * 8 + e * 2;
-              const float f0 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j]), p.param, bb[e * 2], 0.f, p.bias_fused);
-              const float f1 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j + 1]), p.param, bb[e * 2 + 1], 0.f, p.bias_fused);
+              const float f0 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j]), p.param, cb.v[my_bias + h * 32 + j], 0.f, p.bias_fused);
+              const float f1 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j + 1]), p.param, cb.v[my_bias + h * 32 + j + 1], 0.f, p.bias_fused);
               const __half2 hv = __floats2half2_rn(f0, f1);
               w[e] = *reinterpret_cast<const uint32_t*>(&hv);
             }
@@ -498,7 +492,7 @@ conv3x3_pair_trunk_kernel(const __grid_constant__ ConvMaps maps, const ConvParam
               for (int dx = 0; dx < 3; ++dx) {
               if (p.center_only && (dy != 1 || dx != 1)) continue;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 4; ++k) if (k < p.ksteps) {
                   ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 256 + k * 2), idesc, p.center_only ? (k != 0) : ((dy | dx | k) != 0));
                 }
               }

@@ -43,7 +43,7 @@ struct PairHeadCfg {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairHeadThreads, 1)
-conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadParams hp)
+conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadParams hp, const __grid_constant__ ConvBias cb)
 {
   using Cfg = PairHeadCfg;
   constexpr int S = Cfg::kSlots, AS = Cfg::kAccStages, PS = Cfg::kPStages;
@@ -61,11 +61,9 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   const uint32_t staged = tempty + 8 * AS, pfull = staged + 8 * PS, pempty = pfull + 8 * PS;
   const uint32_t wbar = pempty + 8 * PS, wpeer = wbar + 8, dbar = wpeer + 8, tslot = dbar + 8;
   const uint32_t sq_items = bars + 256, sq_bars = bars + 320;       // item queue (kSchedQ ints + kSchedQ barriers), ends at +448
-  const uint32_t bias_sm = bars + 512;                              // 128 floats, 16-byte aligned
   float* xch_ptr = reinterpret_cast<float*>(smem + (bars + 1024 - base));   // P readers' exchange: [2 rows in flight][4 warps][6] floats
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tslot - base));
   uint8_t* stg_ptr = smem + (stg - base);
-  float* bias_ptr = reinterpret_cast<float*>(smem + (bias_sm - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -88,7 +86,6 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&maps.in);
   }
-  for (int i = tid; i < 128; i += kPairHeadThreads) bias_ptr[i] = p.bias[g_fixed * 128 + i];
   if (warp == 1) ptx::tmem_alloc_pair(tslot, Cfg::kTmemCols);
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -168,7 +165,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
               for (int dx = 0; dx < 3; ++dx) {
               if (p.center_only && (dy != 1 || dx != 1)) continue;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 4; ++k) if (k < p.ksteps) {
                   ptx::mma_f16_ss_pair(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, p.center_only ? (k != 0) : ((dy | dx | k) != 0));
                 }
               }
@@ -197,7 +194,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
     const int sw = L & 7;
     const uint32_t tempty_leader = ptx::mapa(tempty, 0);
     const uint32_t staged_leader = ptx::mapa(staged, 0);
-    const float* my_bias = bias_ptr + ch * 64;
+    const int my_bias = (g_fixed * 2 + ch) * 64;                        // index into cb.v (constant bank)
     uint32_t acc = 0;
     uint32_t ord = 0;
     for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
@@ -215,15 +212,12 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 b0 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(my_bias + h * 32 + q * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = q * 8 + e * 2;
-              const float f0 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j]), p.param, bb[e * 2], 0.f, p.bias_fused);
-              const float f1 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j + 1]), p.param, bb[e * 2 + 1], 0.f, p.bias_fused);
+              const float f0 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j]), p.param, cb.v[my_bias + h * 32 + j], 0.f, p.bias_fused);
+              const float f1 = epi_apply<EPI_BIAS_PRELU>(__uint_as_float(v[j + 1]), p.param, cb.v[my_bias + h * 32 + j + 1], 0.f, p.bias_fused);
               const __half2 hv = __floats2half2_rn(f0, f1);
               w[e] = *reinterpret_cast<const uint32_t*>(&hv);
             }
@@ -267,7 +261,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < 4; ++k) if (k < p.ksteps)
                 ptx::mma_f16_ss_pair(tmem_base + Cfg::kPCol0 + ps * 32 + c * 16, a0 + (c * (kStageBytes >> 4) + k * 2), b0 + k * 2, idesc, k != 0);
             ptx::mma_commit_pair_mc(pfull + 8 * ps, 3);
           }

@@ -42,11 +42,21 @@ struct ConvParams {
   float param;            // PReLU slope or residual scale
   int strips, nseg, seg_rows, items;
   int center_only;        // 1: a 1x1 convolution packed as a centre-tap 3x3 filter (MoeNet_lite2): issue only tap (1,1)
+  int ksteps;             // K = 16 * ksteps input channels are real: 4, or 3 for the 48-filter models (NetDN, MoeNet_lite2), whose
+                          // channels 48..63 are exactly zero in every activation — their MMAs are skipped, same bits
   int bias_fused;         // EPI_BIAS_PRELU: 0 = q(q(conv) + bias) (the reference on the GPU), 1 = q(conv + bias) (the half model on the CPU)
   // pair kernels only (conv_pair.cuh, "item scheduler"):
   int dynamic;            // 1: pairs draw their next item from the global counters, 0: round-robin by pair index
   int* sched;             // device int[kSchedInts]: per-chunk-group item counters + the count of finished pairs; all 0 between launches
   unsigned long long* dbg;// optional [pairs][4]: start ns, end ns, SM id, items processed (moe_engine_debug_buffer)
+};
+
+// The bias vector of an upsample convolution as a KERNEL PARAMETER (constant bank): the CTA-pair epilogues need all 64 values of
+// their chunk per pixel; read from shared memory that was 16 LDS.128 per thread and row — as many L1 data-pipe wavefronts as the
+// staging stores of the result, on the pipe the tensor core fetches its operands through (profiles/r02_arsb_experiments.txt).
+// An LDC does not touch that pipe.
+struct ConvBias {
+  float v[9 * 64];        // [r*r chunks][64]
 };
 
 struct ConvMaps {
@@ -213,7 +223,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvParams p)
             for (int dx = 0; dx < 3; ++dx) {
               if (p.center_only && (dy != 1 || dx != 1)) continue;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; ++k) if (k < p.ksteps) {
                 ptx::mma_f16_ss(d_tmem, arow + (dx * 8 + k * 2), bdesc0 + ((dy * 3 + dx) * 512 + k * 2), idesc, p.center_only ? (k != 0) : ((dy | dx | k) != 0));
               }
             }

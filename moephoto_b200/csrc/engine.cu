@@ -63,7 +63,6 @@ struct MoeEngine {
   EncodeTiledFn encode = nullptr;
   std::atomic<int64_t> launches{0};
   int simt = 0;
-  int cur_feat = 64;       // real filter count of the model being run (48 for NetDN) — FLOP accounting only
   bool smem_attr_set = false, head_attr_set = false, pair_attr_set = false;
   int no_pair = 0;         // 1 = keep every conv on the single-CTA kernel (A/B switch)
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
@@ -105,6 +104,7 @@ struct MoeModel {
   const uint8_t* trunk_img[13] = {nullptr};
   const uint8_t* up_img[8] = {nullptr};     // [4*branch + stage]
   const float* up_bias[8] = {nullptr};
+  ConvBias up_bias_h[8];                    // host mirror: the CTA-pair kernels take the bias as a kernel parameter (conv_tc.cuh)
   const float* frm[3] = {nullptr, nullptr, nullptr};   // MoeNet_lite2's FRM gates
   const float* head_w[2] = {nullptr, nullptr};
   uint8_t* d_head_img = nullptr;   // [2][16 rows][128 B] swizzled fp16 image of the two head filters (head_tc.cuh)
@@ -197,15 +197,16 @@ void choose_segments(int64_t base_items, int workers, int H, int min_rows, int* 
 }
 
 // ---- one 3x3 convolution 64 -> 64*r*r ----------------------------------------------------------
+// bias: device vector (single-CTA and SIMT kernels); bias_h: the same values on the host (CTA-pair kernels, as a kernel parameter)
 int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, const __half* skip,
-                const uint8_t* w_img, const float* bias, int N, int H, int W, int r, int epi, float param, int center_only = 0)
+                const uint8_t* w_img, const float* bias, const ConvBias* bias_h, int feat, int N, int H, int W, int r, int epi, float param, int center_only = 0)
 {
   ConvParams p{};
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = out; p.skip = skip;
   p.N = N; p.H = H; p.W = W; p.r = r; p.epi = epi; p.param = param; p.center_only = center_only;
-  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.bias_fused = e->bias_fused;
+  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.ksteps = (feat + 15) / 16; p.bias_fused = e->bias_fused;
   // algorithmic FLOPs: 2 * taps * Cin * Cout per input pixel (padded channels are not counted)
-  Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * r * r) * N * H * W);
+  Timed timed(e, st, r == 1 ? 1 : 3, 2.0 * (center_only ? 1 : 9) * feat * (static_cast<double>(feat) * r * r) * N * H * W);
   if (e->simt) {
     const int64_t threads = static_cast<int64_t>(N) * H * W * r * r * 8;
     conv3x3_simt_kernel<<<grid_for(threads, 256, e->sm_count), 256, 0, st>>>(p);
@@ -291,7 +292,8 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
       e->pair_attr_set = true;
     }
     const int npairs = static_cast<int>(std::min<int64_t>(e->sm_count / 2 / groups * groups, (p.items + groups - 1) / groups * groups));
-    MOE_CUDA(launch_pdl(conv3x3_pair_kernel, 2 * npairs, kConvThreads, PairCfg::kSmemBytes, st, maps, p));
+    if (!bias_h) return fail(MOE_ERR_INVALID, "the CTA-pair convolution needs the host copy of its bias");
+    MOE_CUDA(launch_pdl(conv3x3_pair_kernel, 2 * npairs, kConvThreads, PairCfg::kSmemBytes, st, maps, p, *bias_h));
     return check_launch(e, "conv3x3_pair_kernel");
   }
   typedef void (*ConvFn)(const ConvMaps, const ConvParams);
@@ -307,14 +309,14 @@ int launch_conv(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
 
 // ---- one residual block t' = t + scale * conv_2(PReLU(conv_1(t))) as one kernel (conv_arsb.cuh) ----
 int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, const uint8_t* w1_img, const uint8_t* w2_img,
-                int N, int H, int W, float slope, float scale)
+                int feat, int N, int H, int W, float slope, float scale)
 {
   ArsbParams ap{};
   ConvParams& p = ap.c;
   p.w_img = w1_img; p.in = in; p.out = out; p.N = N; p.H = H; p.W = W; p.r = 1; p.epi = EPI_PRELU; p.param = slope;
-  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg;
+  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.ksteps = (feat + 15) / 16;
   ap.w2_img = w2_img; ap.scale = scale;
-  Timed timed(e, st, 4, 2 * 2.0 * 9 * e->cur_feat * static_cast<double>(e->cur_feat) * N * H * W);   // both convolutions
+  Timed timed(e, st, 4, 2 * 2.0 * 9 * feat * static_cast<double>(feat) * N * H * W);   // both convolutions
   if (e->arsb_solo) {
     if (const char* x = getenv("MOE_ARSB_EXP")) p.center_only = atoi(x);
     // one CTA per SM, full weights of both convolutions per SM (conv_arsb_solo.cuh)
@@ -335,11 +337,12 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the residual block", (int)cr);
     if (!e->arsb_solo_attr_set) {
-      MOE_CUDA(cudaFuncSetAttribute(arsb_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbSoloCfg::kSmemBytes));
+      MOE_CUDA(cudaFuncSetAttribute(arsb_solo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbSoloCfg::kSmemBytes));
+      MOE_CUDA(cudaFuncSetAttribute(arsb_solo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbSoloCfg::kSmemBytes));
       e->arsb_solo_attr_set = true;
     }
     const int grid = static_cast<int>(std::min<int64_t>(e->sm_count, p.items));
-    MOE_CUDA(launch_pdl(arsb_solo_kernel, grid, kArsbSoloThreads, ArsbSoloCfg::kSmemBytes, st, maps, ap));
+    MOE_CUDA(launch_pdl(p.ksteps == 3 ? arsb_solo_kernel<3> : arsb_solo_kernel<4>, grid, kArsbSoloThreads, ArsbSoloCfg::kSmemBytes, st, maps, ap));
     return check_launch(e, "arsb_solo_kernel");
   }
   const int npairs_max = e->sm_count / 2;
@@ -364,29 +367,31 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the residual block", (int)cr);
   if (!e->arsb_attr_set) {
-    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<false>::kSmemBytes));
-    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<true>::kSmemBytes));
+    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<false>::kSmemBytes));
+    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<false>::kSmemBytes));
+    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<true>::kSmemBytes));
+    MOE_CUDA(cudaFuncSetAttribute(arsb_pair_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ArsbCfgT<true>::kSmemBytes));
     e->arsb_attr_set = true;
   }
   const int npairs = static_cast<int>(std::min<int64_t>(npairs_max, p.items));
   if (e->arsb_smem_mid)
-    MOE_CUDA(launch_pdl(arsb_pair_kernel<false>, 2 * npairs, kConvThreads, ArsbCfgT<false>::kSmemBytes, st, maps, ap));
+    MOE_CUDA(launch_pdl(p.ksteps == 3 ? arsb_pair_kernel<false, 3> : arsb_pair_kernel<false, 4>, 2 * npairs, kConvThreads, ArsbCfgT<false>::kSmemBytes, st, maps, ap));
   else
-    MOE_CUDA(launch_pdl(arsb_pair_kernel<true>, 2 * npairs, kConvThreads, ArsbCfgT<true>::kSmemBytes, st, maps, ap));
+    MOE_CUDA(launch_pdl(p.ksteps == 3 ? arsb_pair_kernel<true, 3> : arsb_pair_kernel<true, 4>, 2 * npairs, kConvThreads, ArsbCfgT<true>::kSmemBytes, st, maps, ap));
   return check_launch(e, "arsb_pair_kernel");
 }
 
 // ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
-int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, int N, int H, int W,
+int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, const ConvBias* bias_h, int feat, int N, int H, int W,
                      float slope, const uint8_t* head_img, float* hbuf, float* ebuf, int center_only = 0)
 {
   PairHeadParams hp{};
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
   p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
-  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.bias_fused = e->bias_fused;
+  p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.ksteps = (feat + 15) / 16; p.bias_fused = e->bias_fused;
   hp.head_img = head_img; hp.hbuf = hbuf; hp.ebuf = ebuf;
-  Timed timed(e, st, 5, 2.0 * (center_only ? 1 : 9) * e->cur_feat * (static_cast<double>(e->cur_feat) * 4) * N * H * W);
+  Timed timed(e, st, 5, 2.0 * (center_only ? 1 : 9) * feat * (static_cast<double>(feat) * 4) * N * H * W);
   const int npairs_max = (e->sm_count / 2) & ~1;
   const int strips1 = (W + kStripW - 1) / kStripW;
   p.strips = (strips1 + 1) / 2;
@@ -410,7 +415,7 @@ int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint
     e->pair_head_attr_set = true;
   }
   const int npairs = static_cast<int>(std::min<int64_t>(npairs_max, p.items));
-  MOE_CUDA(launch_pdl(conv3x3_pair_head_kernel, 2 * npairs, kPairHeadThreads, PairHeadCfg::kSmemBytes, st, maps, hp));
+  MOE_CUDA(launch_pdl(conv3x3_pair_head_kernel, 2 * npairs, kPairHeadThreads, PairHeadCfg::kSmemBytes, st, maps, hp, *bias_h));
   return check_launch(e, "conv3x3_pair_head_kernel");
 }
 
@@ -701,7 +706,7 @@ int moe_model_load(MoeEngine* e, int arch, const void* blob, size_t nbytes, MoeM
       case SEC_SCALARS: bad |= en.nbytes != sizeof m->scalars; if (!bad) { memcpy(m->scalars, hb + en.offset, sizeof m->scalars); have_scalars = true; } break;
       case SEC_TRUNK_IMG: bad |= en.index >= 13 || en.nbytes != kChunkImgBytes; if (!bad) { m->trunk_img[en.index] = dp; ++n_trunk; } break;
       case SEC_UP_IMG: bad |= en.index >= 8 || en.nbytes != n_chunks * kChunkImgBytes; if (!bad) { m->up_img[en.index] = dp; ++n_up_img; } break;
-      case SEC_UP_BIAS: bad |= en.index >= 8 || en.nbytes != n_chunks * 64 * 4; if (!bad) { m->up_bias[en.index] = reinterpret_cast<const float*>(dp); ++n_up_bias; } break;
+      case SEC_UP_BIAS: bad |= en.index >= 8 || en.nbytes != n_chunks * 64 * 4; if (!bad) { m->up_bias[en.index] = reinterpret_cast<const float*>(dp); memcpy(m->up_bias_h[en.index].v, hb + en.offset, en.nbytes); ++n_up_bias; } break;
       case SEC_FRM: bad |= en.index >= 3 || en.nbytes != 516 * 4; if (!bad) { m->frm[en.index] = reinterpret_cast<const float*>(dp); ++n_frm; } break;
       case SEC_HEAD_W: bad |= en.index >= 2 || en.nbytes != 9 * 64 * 4; if (!bad) { m->head_w[en.index] = reinterpret_cast<const float*>(dp); ++n_head; } break;
       default: bad = true;
@@ -822,7 +827,6 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     fp.in_h = plan->in_h; fp.in_w = plan->in_w; fp.pad_h = plan->pad_h; fp.pad_w = plan->pad_w;
     fp.top = t.top + g.c0; fp.left = t.left; fp.N = N; fp.H = H; fp.W = W;
     fp.w = m->first_w; fp.slope = m->scalars[0]; fp.out = bufA;
-    e->cur_feat = m->feat;
     if (N > 65535) return fail(MOE_ERR_INVALID, "too many planes for the conv_input grid");
     {
     Timed timed(e, st, 0, static_cast<double>(N) * H * W * (2 + 128));     // bytes: read 1 fp16, write 64 fp16
@@ -834,7 +838,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 
     const int one_by_one = m->arch == MOE_ARCH_LITE;            // MoeNet_lite2: conv_input2 and the upsample convs are 1x1
-    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, N, H, W, 1, EPI_PLAIN, 0.f, one_by_one)) != MOE_OK) return rc;   // conv_input2
+    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PLAIN, 0.f, one_by_one)) != MOE_OK) return rc;   // conv_input2
     if (m->arch == MOE_ARCH_LITE) {
       // three LB blocks: t = FRM(conv_2(PReLU(conv_1(t)))) + t                  MoeNet_lite2.py:7-20, models.py:270-287
       float* partial = reinterpret_cast<float*>(ws + tile_units(m) * unit);
@@ -842,8 +846,8 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
       const int64_t px = static_cast<int64_t>(H) * W;
       for (int b = 0; b < 3; ++b) {
         const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
-        if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
-        if ((rc = launch_conv(e, st, bufM, bufC, nullptr, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, bufM, bufC, nullptr, m->trunk_img[l2], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
         Timed timed(e, st, 6, static_cast<double>(N) * px * 128 * 4);               // bytes: v read twice, t read and written
         frm_partial_kernel<<<dim3(kFrmBlocks, N), 256, 0, st>>>(bufC, partial, px);
         if ((rc = check_launch(e, "frm_partial_kernel")) != MOE_OK) return rc;
@@ -860,11 +864,11 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
       for (int b = 0; b < 6; ++b) {
         const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
         if (fused_arsb) {
-          if ((rc = launch_arsb(e, st, cur, other, m->trunk_img[l1], m->trunk_img[l2], N, H, W, m->scalars[1 + l1], m->scalars[1 + l2])) != MOE_OK) return rc;
+          if ((rc = launch_arsb(e, st, cur, other, m->trunk_img[l1], m->trunk_img[l2], m->feat, N, H, W, m->scalars[1 + l1], m->scalars[1 + l2])) != MOE_OK) return rc;
           std::swap(cur, other);                                 // six blocks: the result ends up in bufT again
         } else {
-          if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
-          if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
+          if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+          if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, nullptr, m->feat, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
         }
       }
     }
@@ -895,10 +899,10 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
           const float* wb = m->up_bias[4 * b + s2];
           const float slope = m->scalars[14 + 4 * b + s2];
           if (last && fuse) {
-            if ((rc = launch_conv_head(e, st, src, wimg, wb, N, hs, wsz, slope, m->d_head_img + b * 2048, hbuf[b], ebuf[b], one_by_one)) != MOE_OK) return rc;
+            if ((rc = launch_conv_head(e, st, src, wimg, wb, &m->up_bias_h[4 * b + s2], m->feat, N, hs, wsz, slope, m->d_head_img + b * 2048, hbuf[b], ebuf[b], one_by_one)) != MOE_OK) return rc;
           } else {
             __half* dst = last ? reinterpret_cast<__half*>(fin + b * fin_units * unit) : stage_buf[s2];
-            if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
+            if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, &m->up_bias_h[4 * b + s2], m->feat, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
             src = dst;
             if (last) head_in[b] = dst;
           }
@@ -908,7 +912,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
       const size_t usz = unit * 9;
       for (int b = 0; b < 2; ++b) {
         __half* dst = reinterpret_cast<__half*>(up0 + b * usz);
-        if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[4 * b], m->up_bias[4 * b], N, H, W, 3,
+        if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[4 * b], m->up_bias[4 * b], &m->up_bias_h[4 * b], m->feat, N, H, W, 3,
                               EPI_BIAS_PRELU, m->scalars[14 + 4 * b])) != MOE_OK) return rc;
         head_in[b] = dst;
       }
@@ -955,8 +959,13 @@ int moe_conv3x3_c64(MoeEngine* e, const void* in, void* out, const void* skip, c
     return fail(MOE_ERR_INVALID, "bad argument");
   if ((epi == EPI_SCALE_SKIP && !skip) || (epi == EPI_BIAS_PRELU && !bias)) return fail(MOE_ERR_INVALID, "epilogue operand missing");
   Guard g(e->device);
+  ConvBias bias_h{};                           // diagnostic entry: the bias comes as a device vector, the pair kernels want it as a parameter
+  if (epi == EPI_BIAS_PRELU) {
+    MOE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    MOE_CUDA(cudaMemcpy(bias_h.v, bias, static_cast<size_t>(r) * r * 64 * sizeof(float), cudaMemcpyDeviceToHost));
+  }
   return launch_conv(e, static_cast<cudaStream_t>(stream), static_cast<const __half*>(in), static_cast<__half*>(out),
-                     static_cast<const __half*>(skip), static_cast<const uint8_t*>(w_img), bias, n, h, w, r, epi, param);
+                     static_cast<const __half*>(skip), static_cast<const uint8_t*>(w_img), bias, &bias_h, 64, n, h, w, r, epi, param);
 }
 
 int moe_axpby_f16(MoeEngine* e, void* y, const void* x, float s, size_t count, void* stream)
