@@ -1,19 +1,21 @@
-// The fused residual block (conv_arsb.cuh) on ONE CTA per SM instead of a CTA pair.
+// The fused residual block (conv_arsb.cuh) on ONE CTA per SM instead of a CTA pair — an A/B variant (engine switch bit 8), slower than
+// the pair form, kept because it is what located the limit of the 64 -> 64 layers (profiles/r02_arsb_experiments.txt).
 //
-// Every N = 64 CTA-pair kernel of this engine runs at 49-54 cycles per MMA where the math takes 32
-// (profiles/r02_arsb_experiments.txt): cta_group::2 splits the B operand, so each SM fetches half of the weights of every MMA
-// from its partner's shared memory.  Measured alone on one SM (tools/mma_ts.cu, profiles/r01_mma_ts_microbench.log) a
-// 128 x 64 x 16 MMA costs 48.5 cycles with both operands in shared memory and 32.3 with A in tensor memory.  This kernel uses
-// exactly those two: conv_1 reads its A operand (the t rows, TMA-loaded) from shared memory, conv_2 reads its A operand (the mid
-// rows, written by the mid epilogue with tcgen05.st as three shifted views) from tensor memory; both keep ALL 64 output channels of
-// their weights in this SM's shared memory (2 x 72 KB).  Expected 36 x 48.5 + 36 x 32.3 = 2 909 cycles per 126-pixel row per SM
-// against 3 800-3 900 per 252-pixel row per SM PAIR.
-// What pays for the doubled weights: no staging tile (the result row leaves as plain 16-byte stores, one full 128-byte line per
-// thread), no mid ring (tensor memory), a 4-slot t ring released by the MMA warp's commits (the residual comes from global memory,
-// an L2 hit: this CTA loaded the row by TMA a few rows earlier).  216 KB of shared memory, all 512 TMEM columns.
-// Rounding points and accumulation order are those of arsb_pair_kernel and of the two-launch form: bit-identical results.
-// Warp roles: 0 TMA producer + item scheduler, 1 conv_1 issuer, 2..5 mid epilogue, 6..9 output epilogue, 10 conv_2 issuer
-// (the two issuers take turns, see there).
+// Built to test the hypothesis that the N = 64 CTA-pair kernels (49-54 cycles per MMA for 32 of math) wait for the half of the B
+// operand that cta_group::2 fetches from the partner SM.  Here every SM holds ALL 64 output channels of both convolutions (2 x 72 KB);
+// conv_1 reads its A operand (the t rows, TMA-loaded) from shared memory, conv_2 reads its A operand (the mid rows, written by the
+// mid epilogue with tcgen05.st as three shifted views) from tensor memory.  Measured in the kernel: the MMAs issue at exactly the
+// single-SM microbenchmark rates (49 cycles .ss, 38 .ts) — and the kernel is still slower than the pair form, because
+//   * tcgen05.mma blocks the issuing thread while the short queue is full and every wait / commit around the MMAs costs that thread
+//     100-250 cycles, so the tensor pipe idles through the bookkeeping (hence two issuing warps that take turns, below), and
+//   * with 144 KB of weights there is no room for a staging tile: the result row leaves as 16-byte global stores, one 128-byte line
+//     per thread, and those 2 000 L1 wavefronts per row compete with the 2 300 wavefronts of the tensor core's operand fetch for
+//     the one-wavefront-per-cycle shared-memory data pipe (without them: 3 760 instead of 4 700 cycles per row).
+// The per-SM operand bytes per MMA are the same as in the pair form (4 KB A + 2 KB B against 4 KB A + 1 KB B + 1 KB served to the
+// partner): the B exchange was never the limit, the A fetch is.
+// 216 KB of shared memory (4-slot t ring released by the MMA warp's commits, residual from global memory = an L2 hit), all 512
+// TMEM columns.  Rounding points and accumulation order are those of arsb_pair_kernel and of the two-launch form: bit-identical.
+// Warp roles: 0 TMA producer + item scheduler, 1 conv_1 issuer, 2..5 mid epilogue, 6..9 output epilogue, 10 conv_2 issuer.
 #pragma once
 #include "conv_arsb.cuh"
 

@@ -53,8 +53,9 @@ struct ConvParams {
 
 // The bias vector of an upsample convolution as a KERNEL PARAMETER (constant bank): the CTA-pair epilogues need all 64 values of
 // their chunk per pixel; read from shared memory that was 16 LDS.128 per thread and row — as many L1 data-pipe wavefronts as the
-// staging stores of the result, on the pipe the tensor core fetches its operands through (profiles/r02_arsb_experiments.txt).
-// An LDC does not touch that pipe.
+// staging stores of the result (106 M of 225 M in conv3x3_pair_head_kernel), on the pipe the tensor core fetches its operands
+// through.  An LDC does not touch that pipe.  (It halved the kernel's LSU share, 31 -> 16 % of cycles, without changing its
+// duration: profiles/r02_arsb_experiments.txt.)
 struct ConvBias {
   float v[9 * 64];        // [r*r chunks][64]
 };

@@ -8,7 +8,9 @@ CLASS_OF = [('arsb_pair_kernel', 'arsb'), ('conv3x3_pair_head_kernel', 'conv_up_
             ('conv3x3_pair_kernel', 'conv_up'), ('conv_first_kernel', 'conv_input'), ('head_stencil_kernel', 'head'), ('head_tc_kernel', 'head_tc')]
 WANT = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
         'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
-        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size', 'sm__cycles_elapsed.max.per_second']
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size', 'sm__cycles_elapsed.max.per_second',
+        # the L1 / shared-memory data pipe (one 128-byte wavefront per cycle): tensor-core operand fetch and every LSU access share it
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed']
 
 
 def unit_scale(u):
@@ -25,7 +27,7 @@ def main():
     ki = hdr.index('Kernel Name')
     lines.append('== %s' % rep)
     for r in rows[2:]:
-      name = r[ki].split('(')[0].replace('moe::', '').replace('void ', '')
+      name = r[ki].replace('(bool)', '').replace('(int)', '').replace('(moe::ConvEpilogue)', '').split('(')[0].replace('moe::', '').replace('void ', '')
       v = {}
       for k in WANT:
         cand = [i for i, h in enumerate(hdr) if h == k or h.endswith('.' + k)]
@@ -35,10 +37,11 @@ def main():
           except ValueError:
             pass
       rd, wr, dur = v.get('dram__bytes_read.sum', 0), v.get('dram__bytes_write.sum', 0), v.get('gpu__time_duration.sum', 0)
-      lines.append('%-34s %9.1f us  %8.0f kcycles @ %.2f GHz | tensor pipe %5.1f %% of elapsed, operand path %5.1f %% | DRAM read %7.3f GB write %7.3f GB = %5.2f TB/s (%4.1f %% of peak) | %3d regs, grid %d'
+      lines.append('%-40s %9.1f us  %8.0f kcycles @ %.2f GHz | tensor pipe %5.1f %% of elapsed, operand path %5.1f %%, L1 data pipe: tensor %4.1f %% + LSU %4.1f %% | DRAM read %7.3f GB write %7.3f GB = %5.2f TB/s (%4.1f %% of peak) | %3d regs, grid %d'
                    % (name, dur * 1e6, v.get('sm__cycles_elapsed.max', 0) / 1e3, v.get('sm__cycles_elapsed.max.per_second', 0),
                       v.get('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 0),
-                      v.get('sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 0), rd / 1e9, wr / 1e9, (rd + wr) / max(dur, 1e-12) / 1e12,
+                      v.get('sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 0),
+                      v.get('l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 0), v.get('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 0), rd / 1e9, wr / 1e9, (rd + wr) / max(dur, 1e-12) / 1e12,
                       v.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 0), int(v.get('launch__registers_per_thread', 0)), int(v.get('launch__grid_size', 0))))
       for key, cls in CLASS_OF:
         if rep != reps[0]:
