@@ -4,13 +4,15 @@
   step   : one frame through runSR.sr(getOpt({'model':'a','scale':4})) — the reference's auto tile plan
            for a 180 GB GPU (4 column strips of 2160x968, pad 5, seam 20 px), every tile through the 20
            convolutions of Net4x, seam-blended and stitched on the device.
-  N GPUs : the SAME frame, canvas rows sharded over the ranks (moephoto_b200/parallel.py): broadcast of
-           the LR frame, per-rank row band + 16-px recompute halo, NCCL gather into rank 0 -> "strong".
+  N GPUs : the SAME frame, canvas rows sharded over the ranks (moephoto_b200/parallel.py):
+           per-rank row band + 16-px recompute halo; every rank reads the frame from and stores its band into
+           rank 0's HBM in place over NVLink peer memory (parallel.BandSharder; no bulk collective) -> "strong".
   value  : frame resident in HBM (fp16 planar) -> stitched fp16 canvas resident in HBM on rank 0; the engine's per-launch
            profiler is OFF in this timed region (the per-kernel breakdown comes from a second pass).
   e2e    : uint8 HWC frame in pinned HOST memory -> uint8 HWC result in HOST memory, through the C-ABI
-           (moe_enhance_host at N=1; at N>1 parallel.sharded_enhance_host: every rank converts and copies its own
-           band into a shared page-locked host frame), copies timed.
+           (moe_enhance_host at N=1; at N>1 parallel.BandSharder.run_host: the uint8 frame is uploaded once into rank 0's HBM,
+           every rank reads it over peer memory, computes its band and copies it into a shared page-locked host frame over its
+           own PCIe link, moe_run_band_to_host), copies timed.
   roofline : the dominant kernel (conv3x3_pair_head_kernel) and, under `kernels`, every kernel class with its own algorithmic
            work (halo rows, padded channels and scrap columns are NOT counted), CUDA-event time, fraction of
            the measured peak and ncu DRAM bytes per launch (profiles/traffic.json, one capture session of this build).
@@ -388,7 +390,7 @@ def main():
     'clocks': clocks,
     'e2e': {'value': e2e_val, 'unit': 'MPix/s', 'ms_per_step': e2e_ms / args.steps, 'h2d_bytes_per_step': H_IN * W_IN * 3,
             'd2h_bytes_per_step': H_IN * SCALE * W_IN * SCALE * 3, 'path': 'moe_enhance_host (C ABI, pinned host uint8 in/out)' if world == 1 else
-            'toTorch on rank 0 -> NCCL broadcast -> per-rank row band -> moe_to_output + D2H of each band into a shared page-locked host frame'},
+            'BandSharder.run_host: H2D of the uint8 frame on rank 0 -> every rank reads it over NVLink peer memory -> per-rank row band -> moe_run_band_to_host: D2H of each band into a shared page-locked host frame over the rank\'s own PCIe link'},
     'gpu_launches': launches,
     'roofline': {'bound': 'tensor', 'kernel': dom.get('kernel'), 'achieved': dom.get('achieved'), 'peak': pk['tflops'], 'unit': 'TFLOP/s',
                  'frac': dom.get('frac'), 'traffic': dom.get('traffic'), 'peak_source': pk['src'],
