@@ -107,13 +107,44 @@ def peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+  """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a thread every 5 ms
+  (the 8-GPU timed region lasts ~120 ms: `nvidia-smi -lms 50` delivered no sample inside it); `nvidia-smi` is the fallback when
+  the NVML binding is missing."""
   Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
   def __init__(self, gpu_index):
+    self.rows, self.skip, self.p, self.f, self.thread = [], 0, None, None, None
+    try:
+      import pynvml, threading
+      pynvml.nvmlInit()
+      try:
+        uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+      except Exception:
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+      self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+      bits = {'hw_slowdown': pynvml.nvmlClocksEventReasonHwSlowdown, 'hw_thermal_slowdown': pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+              'sw_thermal_slowdown': pynvml.nvmlClocksEventReasonSwThermalSlowdown, 'sw_power_cap': pynvml.nvmlClocksEventReasonSwPowerCap}
+      self.running = True
+
+      def poll():
+        while self.running:
+          try:
+            mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append((mhz, [k for k, b in bits.items() if mask & b]))
+          except Exception:
+            pass
+          time.sleep(0.005)
+      self.thread = threading.Thread(target=poll, daemon=True)
+      self.thread.start()
+      self.how = 'NVML polled every 5 ms'
+      return
+    except Exception:
+      self.thread = None
+    self.how = 'nvidia-smi -lms 50'
     self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-    self.p = None
     try:
       self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '50'],
                                 stdout=self.f, stderr=subprocess.DEVNULL)
@@ -121,7 +152,10 @@ class ClockSampler:
       pass
 
   def mark(self):
-    """samples written before this call belong to the warm-up and are dropped"""
+    """samples taken before this call belong to the warm-up and are dropped"""
+    if self.thread:
+      self.skip = len(self.rows)
+      return
     self.f.flush()
     try:
       self.skip = sum(1 for _ in open(self.f.name))
@@ -129,26 +163,31 @@ class ClockSampler:
       self.skip = 0
 
   def stop(self):
-    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-    if self.p is None:
-      return out
-    self.p.terminate()
-    try:
-      self.p.wait(timeout=5)
-    except Exception:
-      self.p.kill()
-    self.f.flush()
-    rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()][getattr(self, 'skip', 0):]
-    os.unlink(self.f.name)
+    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, how=self.how)
     sm, reasons = [], set()
-    for r in rows:
+    if self.thread:
+      self.running = False
+      self.thread.join(timeout=2)
+      out['sm_max_mhz'] = self.max_mhz
+      for mhz, rs in self.rows[self.skip:]:
+        sm.append(mhz); reasons.update(rs)
+    elif self.p is not None:
+      self.p.terminate()
       try:
-        sm.append(float(r[1])); out['sm_max_mhz'] = float(r[2])
+        self.p.wait(timeout=5)
       except Exception:
-        continue
-      for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
-        if v.strip().lower().startswith('active'):
-          reasons.add(name)
+        self.p.kill()
+      self.f.flush()
+      rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()][self.skip:]
+      os.unlink(self.f.name)
+      for r in rows:
+        try:
+          sm.append(float(r[1])); out['sm_max_mhz'] = float(r[2])
+        except Exception:
+          continue
+        for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+          if v.strip().lower().startswith('active'):
+            reasons.add(name)
     if sm:
       sm.sort()
       busy = [v for v in sm if v > 0.5 * sm[-1]] or sm
