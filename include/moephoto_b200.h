@@ -113,7 +113,9 @@ int moe_engine_profile_read(MoeEngine* e, double ms[MOE_PROFILE_CLASSES], double
  *        path computes (aten: cudnn_convolution, then add_ of the bias — two ops, two fp16 roundings), 1 = q(conv + bias), what
  *        the same half model computes on the CPU (oneDNN adds the bias inside the convolution; tests/golden `.ref16`);
  * bit 6: 1 = run every residual block (ARSB) as two convolution launches instead of the fused arsb_pair_kernel;
- * bit 7: 1 = the fused residual block keeps its intermediate rows in shared memory (.ss conv_2) instead of tensor memory (.ts) */
+ * bit 7: 1 = the fused residual block keeps its intermediate rows in shared memory (.ss conv_2) instead of tensor memory (.ts);
+ * bit 8: 1 = the fused residual block on single CTAs with all weights per SM (arsb_solo_kernel) instead of CTA pairs — slower;
+ *        the experiment that located the 64->64 layers' limit (profiles/r02_arsb_experiments.txt) */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
 /* Kernels wait on mbarriers with a time-out (4 s of wall time).  A wait that gives up does NOT trap — round 1's __trap() destroyed
  * the CUDA context of the whole host process, i.e. MoePhoto's worker and every cached model, and a slow wait (a time-sliced or
@@ -151,7 +153,9 @@ int moe_run_plan(MoeModel* m,
 /* 3x3 convolution, 64 -> 64*r*r channels, NHWC fp16 (the building block of ARSB, models.py:76-80, and of
  * genUpsampleBlock, models.py:29-33).  in: (n,h,w,64); out: (n,h*r,w*r,64); w_img: r*r swizzled 73 728-byte
  * images ON THE DEVICE (csrc/blob.h); bias: r*r*64 floats on the device or NULL.
- * epi: 0 plain, 1 PReLU(param), 2 out = skip + param*conv (skip may alias out), 3 PReLU(conv+bias) */
+ * epi: 0 plain, 1 PReLU(param), 2 out = skip + param*conv (skip may alias out), 3 PReLU(conv+bias).
+ * With epi 3 this hook synchronises `stream` and copies the bias to the host (the CTA-pair kernels take it as a kernel
+ * parameter; a loaded model keeps a host copy, so moe_run_plan never does this). */
 int moe_conv3x3_c64(MoeEngine* e, const void* in, void* out, const void* skip, const void* w_img, const float* bias,
                     int n, int h, int w, int r, int epi, float param, void* stream);
 
