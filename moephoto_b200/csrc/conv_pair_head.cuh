@@ -25,9 +25,9 @@
 namespace moe {
 
 struct PairHeadParams {
-  ConvParams c;            // the convolution (r = 2, EPI_BIAS_PRELU); c.out is unused
+  ConvParams c;            // the convolution (r = 2 or 3, EPI_BIAS_PRELU); c.out is unused
   const uint8_t* head_img; // [16 rows][128 B] swizzled fp16: rows 0..8 = the 9 taps of THIS branch's head filter
-  float* hbuf;             // [N][3][2H][2W] fp32: this branch's H_dy planes
+  float* hbuf;             // r = 2: [N][3][2H][2W] fp32, this branch's H_dy planes; r = 3: [N][H][9 chunks x 9 taps][W] fp32 dot products
   float* ebuf;             // [N][2H][2 * strips][6] fp32: per CTA strip and output row, {first pixel's P[dy,2], last pixel's P[dy,0]}
 };
 
@@ -69,9 +69,10 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader_cta = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int g_fixed = pair & 1;                   // npairs is even (host): a pair keeps its chunk group
-  const int my_chunk = g_fixed * 2 + static_cast<int>(rank);
-  const PairSched sc = sched_make(p, sq_items, sq_bars, pair, npairs, 2);
+  const int groups = pair_groups(p.r), nchunks = p.r * p.r;   // 2 chunk groups for PixelShuffle(2), 5 for PixelShuffle(3)
+  const int g_fixed = pair % groups;              // npairs is a multiple of the group count (host): a pair keeps its chunk group
+  const int my_chunk = min(g_fixed * 2 + static_cast<int>(rank), nchunks - 1);   // the idle half of PixelShuffle(3)'s last group recomputes chunk 8
+  const PairSched sc = sched_make(p, sq_items, sq_bars, pair, npairs, groups);
   const uint64_t t_start = p.dbg ? ptx::globaltimer_ns() : 0;
   int n_items = 0;
 
@@ -194,7 +195,7 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
     const int sw = L & 7;
     const uint32_t tempty_leader = ptx::mapa(tempty, 0);
     const uint32_t staged_leader = ptx::mapa(staged, 0);
-    const int my_bias = (g_fixed * 2 + ch) * 64;                        // index into cb.v (constant bank)
+    const int my_bias = min(g_fixed * 2 + ch, nchunks - 1) * 64;        // index into cb.v (constant bank)
     uint32_t acc = 0;
     uint32_t ord = 0;
     for (int item = sched_take(sc, ord++); item >= 0; item = sched_take(sc, ord++)) {
@@ -299,6 +300,22 @@ conv3x3_pair_head_kernel(const __grid_constant__ ConvMaps maps, const PairHeadPa
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(pempty_leader + 8 * ps);
+        if (p.r == 3) {
+          // PixelShuffle(3): the three sub-pixels of an output row sit in different chunk groups (= different CTA pairs), so
+          // no horizontal sum here.  The nine dot products of each sub-pixel chunk leave at INPUT resolution as
+          // pbuf[n][y][chunk * 9 + tap][W]: full 128-byte lines per warp, and the 81 row segments of an input row adjacent in
+          // memory (as 81 separate planes head_stencil9_kernel read 243 DRAM pages at once and ran at a quarter of the HBM rate).
+          if (valid) {
+            float* dst = hp.hbuf + ((static_cast<size_t>(n) * p.H + y) * 81 + g_fixed * 18) * p.W + x;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) dst[t * p.W] = __uint_as_float(v0[t]);
+            if (g_fixed * 2 + 1 < nchunks) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) dst[(9 + t) * p.W] = __uint_as_float(v1[t]);
+            }
+          }
+          continue;
+        }
         // chunk c of this pair's group g is sub-pixel (i, j) = (g, c): v0 = output pixel (2y + g, 2x), v1 = (2y + g, 2x + 1)
         float c0[9], c1[9];
 #pragma unroll
@@ -434,6 +451,77 @@ __global__ void __launch_bounds__(kStencilThreads) head_stencil_kernel(const Hea
     } else {
 #pragma unroll
       for (int i = 0; i < kStencilPx; ++i) if (keep[i]) dst[i] = __float2half_rn(out[i]);
+    }
+  }
+}
+
+// PixelShuffle(3) (a3 = Net3x, models.py:135-143): the fused convolution leaves, per branch, the nine dot products
+// P_t = <w_head[t], act> of every output pixel at input resolution, pbuf[n][y][chunk (i,j) * 9 + tap][w] with output pixel
+// (3y + i, 3x + j).  out(Y,X) = round16(round16(S_u) + round16(S_r)), S = sum over taps (dy,dx) of P_(dy,dx)(Y+dy-1, X+dx-1) in the
+// order of head_stencil_kernel: ((P_dy0 + P_dy1) + P_dy2) per dy, then (H_0 + H_1) + H_2; zero outside the computed rectangle.  A
+// thread owns one input pixel = a 3 x 3 block of outputs: 81 loads per branch, every one a full line per warp; 72 B per output
+// pixel instead of the 256 B the unfused head reads.  Then the seam blend and canvas store of the other head kernels.
+struct HeadStencil9Params {
+  HeadParams g;            // geometry at OUTPUT resolution (g.H = 3h, g.W = 3w), seam and canvas (u/r/wu/wr unused)
+  const float* pu;         // [N][h][81][w]
+  const float* pr;
+  int h, w;
+};
+
+__global__ void __launch_bounds__(128) head_stencil9_kernel(const HeadStencil9Params p)
+{
+  const HeadParams& g = p.g;
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int n = blockIdx.z;
+  if (x >= p.w) return;
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  const float* pb[2] = {p.pu + static_cast<size_t>(n) * 81 * plane, p.pr + static_cast<size_t>(n) * 81 * plane};
+  for (int y = blockIdx.y; y < p.h; y += gridDim.y) {
+    if (g.oy + 3 * y + 2 < g.keep_y0 || g.oy + 3 * y >= g.keep_y1) continue;
+    float head[2][9];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float hsum[3];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int a = i + dy - 1;                                  // output row 3y + a: input row y + oyy, sub-pixel row ii
+            const int oyy = a < 0 ? -1 : (a > 2 ? 1 : 0), ii = (a + 3) % 3;
+            const int yy = y + oyy;
+            float term[3];
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int c = j + dx - 1;
+              const int oxx = c < 0 ? -1 : (c > 2 ? 1 : 0), jj = (c + 3) % 3;
+              const int xx = x + oxx;
+              const bool in = yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+              term[dx] = in ? __ldg(pb[b] + (static_cast<size_t>(yy) * 81 + ((ii * 3 + jj) * 9 + dy * 3 + dx)) * p.w + xx) : 0.f;
+            }
+            hsum[dy] = (term[0] + term[1]) + term[2];
+          }
+          head[b][i * 3 + j] = h_round((hsum[0] + hsum[1]) + hsum[2]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int cy = g.oy + 3 * y + i;
+      if (cy < g.keep_y0 || cy >= g.keep_y1) continue;
+      __half* dst = g.canvas + n * g.plane_stride + static_cast<int64_t>(cy) * g.row_stride + (g.ox + 3 * x);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int cx = g.ox + 3 * x + j;
+        if (cx < g.keep_x0 || cx >= g.keep_x1) continue;
+        float v = h_round(head[0][i * 3 + j] + head[1][i * 3 + j]);   // u + convt_R1(t), models.py:38
+        if (cy < g.blend_y1 || cx < g.blend_x1) {
+          const float old = __half2float(dst[j]);
+          if (cy < g.blend_y1) v = h_round(old + h_round(g.ramp[cy - g.ramp_y0] * h_round(v - old)));
+          if (cx < g.blend_x1) v = h_round(old + h_round(g.ramp[cx - g.ramp_x0] * h_round(v - old)));
+        }
+        dst[j] = __float2half_rn(v);
+      }
     }
   }
 }

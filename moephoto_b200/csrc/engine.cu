@@ -383,19 +383,20 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
 
 // ---- last upsample conv of a branch fused with the head's dot products (conv_pair_head.cuh) ----
 int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint8_t* w_img, const float* bias, const ConvBias* bias_h, int feat, int N, int H, int W,
-                     float slope, const uint8_t* head_img, float* hbuf, float* ebuf, int center_only = 0)
+                     int r, float slope, const uint8_t* head_img, float* hbuf, float* ebuf, int center_only = 0)
 {
   PairHeadParams hp{};
   ConvParams& p = hp.c;
   p.w_img = w_img; p.bias = bias; p.in = in; p.out = nullptr; p.skip = nullptr;
-  p.N = N; p.H = H; p.W = W; p.r = 2; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
+  p.N = N; p.H = H; p.W = W; p.r = r; p.epi = EPI_BIAS_PRELU; p.param = slope; p.center_only = center_only;
   p.dynamic = !e->static_sched; p.sched = next_sched_block(e); p.dbg = e->dbg; p.ksteps = (feat + 15) / 16; p.bias_fused = e->bias_fused;
   hp.head_img = head_img; hp.hbuf = hbuf; hp.ebuf = ebuf;
-  Timed timed(e, st, 5, 2.0 * (center_only ? 1 : 9) * feat * (static_cast<double>(feat) * 4) * N * H * W);
-  const int npairs_max = (e->sm_count / 2) & ~1;
+  Timed timed(e, st, 5, 2.0 * (center_only ? 1 : 9) * feat * (static_cast<double>(feat) * r * r) * N * H * W);
+  const int groups = pair_groups(r);                          // 2 for PixelShuffle(2), 5 for PixelShuffle(3)
+  const int npairs_max = e->sm_count / 2 / groups * groups;   // a multiple of the group count: a pair keeps its chunk group
   const int strips1 = (W + kStripW - 1) / kStripW;
   p.strips = (strips1 + 1) / 2;
-  const int64_t base_items = 2ll * N * p.strips;
+  const int64_t base_items = static_cast<int64_t>(groups) * N * p.strips;
   choose_segments(base_items, npairs_max, H, 8, &p.seg_rows, &p.nseg);
   const int64_t items = base_items * p.nseg;
   if (items > 0x7fffffff) return fail(MOE_ERR_INVALID, "conv problem too large");
@@ -414,7 +415,7 @@ int launch_conv_head(MoeEngine* e, cudaStream_t st, const __half* in, const uint
     MOE_CUDA(cudaFuncSetAttribute(conv3x3_pair_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairHeadCfg::kSmemBytes));
     e->pair_head_attr_set = true;
   }
-  const int npairs = static_cast<int>(std::min<int64_t>(npairs_max, p.items));
+  const int npairs = static_cast<int>(std::min<int64_t>(npairs_max, (p.items + groups - 1) / groups * groups));
   MOE_CUDA(launch_pdl(conv3x3_pair_head_kernel, 2 * npairs, kPairHeadThreads, PairHeadCfg::kSmemBytes, st, maps, hp, *bias_h));
   return check_launch(e, "conv3x3_pair_head_kernel");
 }
@@ -875,7 +876,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
 
     // the two upsample stacks: branch 0 on `out`, branch 1 on the trunk           models.py:29-33,125-154; MoeNet_lite2.py:47-50
     const __half* head_in[2] = {bufA, bufT};
-    const bool fuse = !e->simt && !e->no_pair && !e->no_fuse && m->n_up >= 1 && m->r == 2 && e->sm_count >= 4;
+    const bool fuse = !e->simt && !e->no_pair && !e->no_fuse && m->n_up >= 1 && e->sm_count / 2 >= pair_groups(m->r);
     float* hbuf[2] = {nullptr, nullptr};
     float* ebuf[2] = {nullptr, nullptr};
     int estrips = 0;
@@ -899,7 +900,7 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
           const float* wb = m->up_bias[4 * b + s2];
           const float slope = m->scalars[14 + 4 * b + s2];
           if (last && fuse) {
-            if ((rc = launch_conv_head(e, st, src, wimg, wb, &m->up_bias_h[4 * b + s2], m->feat, N, hs, wsz, slope, m->d_head_img + b * 2048, hbuf[b], ebuf[b], one_by_one)) != MOE_OK) return rc;
+            if ((rc = launch_conv_head(e, st, src, wimg, wb, &m->up_bias_h[4 * b + s2], m->feat, N, hs, wsz, 2, slope, m->d_head_img + b * 2048, hbuf[b], ebuf[b], one_by_one)) != MOE_OK) return rc;
           } else {
             __half* dst = last ? reinterpret_cast<__half*>(fin + b * fin_units * unit) : stage_buf[s2];
             if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, &m->up_bias_h[4 * b + s2], m->feat, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
@@ -912,6 +913,12 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
       const size_t usz = unit * 9;
       for (int b = 0; b < 2; ++b) {
         __half* dst = reinterpret_cast<__half*>(up0 + b * usz);
+        if (fuse) {                                                // 81 floats per input pixel-plane (324 of the 1 152 B) per branch
+          hbuf[b] = reinterpret_cast<float*>(dst);
+          if ((rc = launch_conv_head(e, st, b ? bufT : bufA, m->up_img[4 * b], m->up_bias[4 * b], &m->up_bias_h[4 * b], m->feat, N, H, W, 3,
+                                     m->scalars[14 + 4 * b], m->d_head_img + b * 2048, hbuf[b], nullptr)) != MOE_OK) return rc;
+          continue;
+        }
         if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[4 * b], m->up_bias[4 * b], &m->up_bias_h[4 * b], m->feat, N, H, W, 3,
                               EPI_BIAS_PRELU, m->scalars[14 + 4 * b])) != MOE_OK) return rc;
         head_in[b] = dst;
@@ -928,7 +935,14 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     for (int i = 0; i < plan->pad_sc; ++i) hp.ramp[i] = plan->ramp[i];
     hp.canvas = static_cast<__half*>(canvas);
     hp.plane_stride = out_plane_stride; hp.row_stride = out_row_stride;
-    if (fuse) {
+    if (fuse && m->r == 3) {
+      HeadStencil9Params sp{};
+      sp.g = hp; sp.pu = hbuf[0]; sp.pr = hbuf[1]; sp.h = H; sp.w = W;
+      dim3 sgrid((W + 127) / 128, std::min(H, 65535), N);
+      if (sgrid.z > 65535u) return fail(MOE_ERR_INVALID, "too many planes for the stencil kernel grid");
+      Timed timed(e, st, 2, static_cast<double>(N) * hp.H * hp.W * (72 + 2));   // bytes: two 9-float reads, one fp16 write
+      head_stencil9_kernel<<<sgrid, 128, 0, st>>>(sp);
+    } else if (fuse) {
       HeadStencilParams sp{};
       sp.g = hp; sp.hu = hbuf[0]; sp.hr = hbuf[1]; sp.eu = ebuf[0]; sp.er = ebuf[1]; sp.estrips = estrips;
       dim3 sgrid((hp.W + kStencilThreads * kStencilPx - 1) / (kStencilThreads * kStencilPx), std::min(hp.H, 65535), N);

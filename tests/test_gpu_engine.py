@@ -378,7 +378,7 @@ def test_chained_dn_then_sr_on_a_frame_batch_16bit_route(engine):
 
 
 @pytest.mark.parametrize('flags', [dict(no_pair=True), dict(no_pair_trunk=True), dict(no_fuse=True), dict(static_sched=True), dict(no_arsb=True), dict(arsb_smem_mid=True), dict(arsb_solo=True)])
-@pytest.mark.parametrize('name', ['a2_tiled', 'a4_tiled', 'lite2_tiled', 'lite8_single'])
+@pytest.mark.parametrize('name', ['a2_tiled', 'a3_tiled', 'a4_tiled', 'lite2_tiled', 'lite8_single'])
 def test_every_tensor_core_kernel_variant_meets_the_same_bar(engine, name, flags):
     """the A/B switches keep the single-CTA conv kernel, the unfused CTA-pair kernel and head_tc_kernel alive;
     each variant is held to the same tolerance as the default path (CTA pairs + fused head)"""
