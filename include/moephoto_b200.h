@@ -115,7 +115,9 @@ int moe_engine_profile_read(MoeEngine* e, double ms[MOE_PROFILE_CLASSES], double
  * bit 6: 1 = run every residual block (ARSB) as two convolution launches instead of the fused arsb_pair_kernel;
  * bit 7: 1 = the fused residual block keeps its intermediate rows in shared memory (.ss conv_2) instead of tensor memory (.ts);
  * bit 8: 1 = the fused residual block on single CTAs with all weights per SM (arsb_solo_kernel) instead of CTA pairs — slower;
- *        the experiment that located the 64->64 layers' limit (profiles/r02_arsb_experiments.txt) */
+ *        the experiment that located the 64->64 layers' limit (profiles/r02_arsb_experiments.txt);
+ * bit 9: 1 = NetDN / MoeNet_lite2 (48 filters, zero-padded to 64) issue all four K steps of every tap instead of skipping the
+ *        all-zero fourth one (test switch: the results are bit-identical) */
 int moe_engine_set_conv_path(MoeEngine* e, int simt);
 /* Kernels wait on mbarriers with a time-out (4 s of wall time).  A wait that gives up does NOT trap — round 1's __trap() destroyed
  * the CUDA context of the whole host process, i.e. MoePhoto's worker and every cached model, and a slow wait (a time-sliced or

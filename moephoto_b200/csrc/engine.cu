@@ -68,6 +68,7 @@ struct MoeEngine {
   int no_pair_trunk = 0;   // 1 = only the 64->64 convs stay on the single-CTA kernel
   int no_fuse = 0;         // 1 = last upsample conv and heads stay separate kernels (conv3x3_pair_kernel + head_tc_kernel)
   int arsb_smem_mid = 0;   // 1 = the fused residual block keeps its mid rows in shared memory (.ss conv_2) instead of TMEM (.ts)
+  int full_k = 0;          // 1 = the 48-filter models issue all four K steps per tap like the 64-filter ones (test switch: same bits)
   int arsb_solo = 0;       // 1 = the fused residual block on single CTAs with full weights per SM (conv_arsb_solo.cuh) instead of CTA pairs
   int no_arsb = 0;         // 1 = every residual block as two launches of the trunk kernel instead of arsb_pair_kernel (A/B switch)
   bool arsb_attr_set = false;
@@ -627,6 +628,7 @@ int moe_engine_set_conv_path(MoeEngine* e, int simt)
   e->no_arsb = (simt >> 6) & 1;
   e->arsb_smem_mid = (simt >> 7) & 1;
   e->arsb_solo = (simt >> 8) & 1;
+  e->full_k = (simt >> 9) & 1;
   return MOE_OK;
 }
 
@@ -838,8 +840,9 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
     }
     if ((rc = check_launch(e, "conv_first_kernel")) != MOE_OK) return rc;
 
+    const int feat = e->full_k ? 64 : m->feat;                  // real input channels per tap (K steps of 16); full_k: test switch
     const int one_by_one = m->arch == MOE_ARCH_LITE;            // MoeNet_lite2: conv_input2 and the upsample convs are 1x1
-    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PLAIN, 0.f, one_by_one)) != MOE_OK) return rc;   // conv_input2
+    if ((rc = launch_conv(e, st, bufA, bufT, nullptr, m->trunk_img[0], nullptr, nullptr, feat, N, H, W, 1, EPI_PLAIN, 0.f, one_by_one)) != MOE_OK) return rc;   // conv_input2
     if (m->arch == MOE_ARCH_LITE) {
       // three LB blocks: t = FRM(conv_2(PReLU(conv_1(t)))) + t                  MoeNet_lite2.py:7-20, models.py:270-287
       float* partial = reinterpret_cast<float*>(ws + tile_units(m) * unit);
@@ -847,8 +850,8 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
       const int64_t px = static_cast<int64_t>(H) * W;
       for (int b = 0; b < 3; ++b) {
         const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
-        if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
-        if ((rc = launch_conv(e, st, bufM, bufC, nullptr, m->trunk_img[l2], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, nullptr, feat, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+        if ((rc = launch_conv(e, st, bufM, bufC, nullptr, m->trunk_img[l2], nullptr, nullptr, feat, N, H, W, 1, EPI_PLAIN, 0.f)) != MOE_OK) return rc;
         Timed timed(e, st, 6, static_cast<double>(N) * px * 128 * 4);               // bytes: v read twice, t read and written
         frm_partial_kernel<<<dim3(kFrmBlocks, N), 256, 0, st>>>(bufC, partial, px);
         if ((rc = check_launch(e, "frm_partial_kernel")) != MOE_OK) return rc;
@@ -865,11 +868,11 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
       for (int b = 0; b < 6; ++b) {
         const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;
         if (fused_arsb) {
-          if ((rc = launch_arsb(e, st, cur, other, m->trunk_img[l1], m->trunk_img[l2], m->feat, N, H, W, m->scalars[1 + l1], m->scalars[1 + l2])) != MOE_OK) return rc;
+          if ((rc = launch_arsb(e, st, cur, other, m->trunk_img[l1], m->trunk_img[l2], feat, N, H, W, m->scalars[1 + l1], m->scalars[1 + l2])) != MOE_OK) return rc;
           std::swap(cur, other);                                 // six blocks: the result ends up in bufT again
         } else {
-          if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, nullptr, m->feat, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
-          if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, nullptr, m->feat, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
+          if ((rc = launch_conv(e, st, bufT, bufM, nullptr, m->trunk_img[l1], nullptr, nullptr, feat, N, H, W, 1, EPI_PRELU, m->scalars[1 + l1])) != MOE_OK) return rc;
+          if ((rc = launch_conv(e, st, bufM, bufT, bufT, m->trunk_img[l2], nullptr, nullptr, feat, N, H, W, 1, EPI_SCALE_SKIP, m->scalars[1 + l2])) != MOE_OK) return rc;
         }
       }
     }
@@ -900,10 +903,10 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
           const float* wb = m->up_bias[4 * b + s2];
           const float slope = m->scalars[14 + 4 * b + s2];
           if (last && fuse) {
-            if ((rc = launch_conv_head(e, st, src, wimg, wb, &m->up_bias_h[4 * b + s2], m->feat, N, hs, wsz, 2, slope, m->d_head_img + b * 2048, hbuf[b], ebuf[b], one_by_one)) != MOE_OK) return rc;
+            if ((rc = launch_conv_head(e, st, src, wimg, wb, &m->up_bias_h[4 * b + s2], feat, N, hs, wsz, 2, slope, m->d_head_img + b * 2048, hbuf[b], ebuf[b], one_by_one)) != MOE_OK) return rc;
           } else {
             __half* dst = last ? reinterpret_cast<__half*>(fin + b * fin_units * unit) : stage_buf[s2];
-            if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, &m->up_bias_h[4 * b + s2], m->feat, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
+            if ((rc = launch_conv(e, st, src, dst, nullptr, wimg, wb, &m->up_bias_h[4 * b + s2], feat, N, hs, wsz, 2, EPI_BIAS_PRELU, slope, one_by_one)) != MOE_OK) return rc;
             src = dst;
             if (last) head_in[b] = dst;
           }
@@ -915,11 +918,11 @@ int run_plan_core(MoeModel* m, const void* in, int64_t in_plane_stride, int64_t 
         __half* dst = reinterpret_cast<__half*>(up0 + b * usz);
         if (fuse) {                                                // 81 floats per input pixel-plane (324 of the 1 152 B) per branch
           hbuf[b] = reinterpret_cast<float*>(dst);
-          if ((rc = launch_conv_head(e, st, b ? bufT : bufA, m->up_img[4 * b], m->up_bias[4 * b], &m->up_bias_h[4 * b], m->feat, N, H, W, 3,
+          if ((rc = launch_conv_head(e, st, b ? bufT : bufA, m->up_img[4 * b], m->up_bias[4 * b], &m->up_bias_h[4 * b], feat, N, H, W, 3,
                                      m->scalars[14 + 4 * b], m->d_head_img + b * 2048, hbuf[b], nullptr)) != MOE_OK) return rc;
           continue;
         }
-        if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[4 * b], m->up_bias[4 * b], &m->up_bias_h[4 * b], m->feat, N, H, W, 3,
+        if ((rc = launch_conv(e, st, b ? bufT : bufA, dst, nullptr, m->up_img[4 * b], m->up_bias[4 * b], &m->up_bias_h[4 * b], feat, N, H, W, 3,
                               EPI_BIAS_PRELU, m->scalars[14 + 4 * b])) != MOE_OK) return rc;
         head_in[b] = dst;
       }

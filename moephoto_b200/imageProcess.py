@@ -68,11 +68,11 @@ class Engine:
     d['conv3x3'] = add('conv_trunk', 'arsb', 'conv_up', 'conv_up_head')
     return d
 
-  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False, static_sched=False, bias_fused=False, no_arsb=False, arsb_smem_mid=False, arsb_solo=False):
+  def set_conv_path(self, simt=False, no_pair=False, no_pair_trunk=False, no_fuse=False, static_sched=False, bias_fused=False, no_arsb=False, arsb_smem_mid=False, arsb_solo=False, full_k=False):
     """A/B switches of the engine.  bias_fused: biased convolutions round once, q(conv + bias), as when the reference's half
     model is executed on the CPU (how the `.ref16` goldens were made); default = the GPU's q(q(conv) + bias)."""
     _lib.check(self.lib.moe_engine_set_conv_path(self.handle, int(bool(simt)) | (int(bool(no_pair)) << 1) | (int(bool(no_pair_trunk)) << 2) |
-                                                 (int(bool(no_fuse)) << 3) | (int(bool(static_sched)) << 4) | (int(bool(bias_fused)) << 5) | (int(bool(no_arsb)) << 6) | (int(bool(arsb_smem_mid)) << 7) | (int(bool(arsb_solo)) << 8)))
+                                                 (int(bool(no_fuse)) << 3) | (int(bool(static_sched)) << 4) | (int(bool(bias_fused)) << 5) | (int(bool(no_arsb)) << 6) | (int(bool(arsb_smem_mid)) << 7) | (int(bool(arsb_solo)) << 8) | (int(bool(full_k)) << 9)))
 
   def debug_buffer(self, tensor):
     """tensor: int64 CUDA tensor of >= 4 values per SM pair, or None; see moe_engine_debug_buffer"""

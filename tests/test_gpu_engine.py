@@ -585,6 +585,20 @@ def test_fused_residual_block_is_bit_identical_to_its_two_launch_form(engine, ke
         config.freeMemOverride = None
 
 
+@pytest.mark.parametrize('name', ['dn15_tiled', 'dn5_single_rgba', 'lite2_tiled', 'lite8_single'])
+def test_skipping_the_zero_k_step_of_48_filter_models_changes_no_bit(engine, name):
+    """NetDN and MoeNet_lite2 have 48 filters zero-padded to 64: channels 48..63 of every activation are exactly 0, so the kernels
+    skip the fourth K step (16 channels) of every tap (ConvParams::ksteps).  `full_k` issues it anyway: same bits"""
+    c = H.load_case(name)
+    y = H.run_case_engine(c)
+    engine.set_conv_path(full_k=True)
+    try:
+        y4 = H.run_case_engine(c)
+    finally:
+        engine.set_conv_path()
+    assert np.array_equal(y, y4)
+
+
 def test_two_streams_share_an_engine(engine):
     """every pair-kernel launch draws its items from its own counter block and the FRM scratch lives in the caller's
     workspace, so two plans may run concurrently on two streams of one engine (two workspaces): results equal the serial ones"""

@@ -4,7 +4,7 @@ One line per captured launch (duration, cycles, tensor pipe, DRAM bytes and thro
 dram__bytes_read.sum + dram__bytes_write.sum per launch keyed by the engine profiler's kernel class (bench.py `roofline.traffic`)."""
 import csv, io, json, subprocess, sys
 
-CLASS_OF = [('arsb_pair_kernel', 'arsb'), ('conv3x3_pair_head_kernel', 'conv_up_head'), ('conv3x3_pair_trunk_kernel', 'conv_trunk'),
+CLASS_OF = [('head_stencil9_kernel', 'head9'), ('arsb_pair_kernel', 'arsb'), ('conv3x3_pair_head_kernel', 'conv_up_head'), ('conv3x3_pair_trunk_kernel', 'conv_trunk'),
             ('conv3x3_pair_kernel', 'conv_up'), ('conv_first_kernel', 'conv_input'), ('head_stencil_kernel', 'head'), ('head_tc_kernel', 'head_tc')]
 WANT = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
         'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
