@@ -319,7 +319,7 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   ap.w2_img = w2_img; ap.scale = scale;
   Timed timed(e, st, 4, 2 * 2.0 * 9 * feat * static_cast<double>(feat) * N * H * W);   // both convolutions
   if (e->arsb_solo) {
-    if (const char* x = getenv("MOE_ARSB_EXP")) p.center_only = atoi(x);
+    if (const char* x = getenv("MOE_ARSB_EXP")) p.center_only = atoi(x) != 0;   // in-kernel cycle accounting of the MMA warps into the debug buffer (tools/arsb_waits.py)
     // one CTA per SM, full weights of both convolutions per SM (conv_arsb_solo.cuh)
     p.strips = (W + kArsbStripW - 1) / kArsbStripW;
     const int64_t base_items = static_cast<int64_t>(N) * p.strips;

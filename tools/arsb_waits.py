@@ -1,5 +1,5 @@
-"""Where the MMA warp of the single-CTA fused residual block waits (MOE_ARSB_EXP bit 4 = in-kernel clock64 accounting):
-   MOE_ARSB_EXP=16 python tools/arsb_waits.py"""
+"""Where the MMA warp of the single-CTA fused residual block waits (MOE_ARSB_EXP=1 switches the in-kernel clock64 accounting on):
+   MOE_ARSB_EXP=1 python tools/arsb_waits.py"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
