@@ -80,6 +80,7 @@ struct MoeEngine {
   int* d_sched = nullptr;
   std::atomic<uint32_t> sched_seq{0};
   std::mutex host_mutex;   // moe_enhance_host: the engine-owned staging buffers serve one call at a time
+  size_t dbg_bytes = 0;
   unsigned long long* dbg = nullptr;   // moe_engine_debug_buffer: per-pair {start ns, end ns, SM id, items} of the LAST pair-kernel launch
   bool pair_head_attr_set = false;
   bool pair_trunk_attr_set = false;
@@ -319,7 +320,8 @@ int launch_arsb(MoeEngine* e, cudaStream_t st, const __half* in, __half* out, co
   ap.w2_img = w2_img; ap.scale = scale;
   Timed timed(e, st, 4, 2 * 2.0 * 9 * feat * static_cast<double>(feat) * N * H * W);   // both convolutions
   if (e->arsb_solo) {
-    if (const char* x = getenv("MOE_ARSB_EXP")) p.center_only = atoi(x) != 0;   // in-kernel cycle accounting of the MMA warps into the debug buffer (tools/arsb_waits.py)
+    // in-kernel cycle accounting of the MMA warps: 8 CTAs x 12 values behind the per-pair records of the debug buffer (tools/arsb_waits.py)
+    if (const char* x = getenv("MOE_ARSB_EXP")) p.center_only = atoi(x) != 0 && e->dbg_bytes >= (74 * 4 + 96) * sizeof(unsigned long long);
     // one CTA per SM, full weights of both convolutions per SM (conv_arsb_solo.cuh)
     p.strips = (W + kArsbStripW - 1) / kArsbStripW;
     const int64_t base_items = static_cast<int64_t>(N) * p.strips;
@@ -662,6 +664,7 @@ int moe_engine_debug_buffer(MoeEngine* e, void* dev, size_t nbytes)
   if (dev && nbytes < static_cast<size_t>(e->sm_count / 2) * 4 * sizeof(unsigned long long))
     return fail(MOE_ERR_INVALID, "debug buffer needs %zu bytes", static_cast<size_t>(e->sm_count / 2) * 4 * sizeof(unsigned long long));
   e->dbg = static_cast<unsigned long long*>(dev);
+  e->dbg_bytes = dev ? nbytes : 0;
   return MOE_OK;
 }
 
