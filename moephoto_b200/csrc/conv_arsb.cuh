@@ -81,6 +81,9 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
 {
   using Cfg = ArsbCfgT<kMidTmem>;
   constexpr int TS = Cfg::kTSlots, MS = Cfg::kMSlots, AS = Cfg::kAcc;
+  // the 48-filter models: N = 48 output channels per MMA as well as K = 48 (their channels 48..63 are zero in and must be zero out);
+  // cta_group::2 takes half of B from each CTA: 24 of the tap's 64 weight rows, three whole swizzle groups
+  constexpr int kN = KS == 3 ? 48 : 64, kHalf = kN / 2;
   const ConvParams& p = ap.c;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -135,10 +138,11 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
   ptx::grid_dep_launch();
   if (warp == 0) {                                 // weights before the dependency wait (see conv3x3_pair_kernel)
     if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(wbar, 2 * Cfg::kWBytes);
-      for (int tap = 0; tap < 9; ++tap) {      // output channels 32*rank .. +31 of every tap, both convolutions
-        ptx::bulk_load_1d(w1sm + tap * 4096, p.w_img + tap * 8192 + rank * 4096, 4096, wbar);
-        ptx::bulk_load_1d(w2sm + tap * 4096, ap.w2_img + tap * 8192 + rank * 4096, 4096, wbar);
+      // output channels kHalf*rank .. +kHalf-1 of every tap, both convolutions (rows of 128 B in 8-row swizzle groups of 1 KB)
+      ptx::mbar_expect_tx(wbar, 2 * 9 * kHalf * 128);
+      for (int tap = 0; tap < 9; ++tap) {
+        ptx::bulk_load_1d(w1sm + tap * 4096, p.w_img + tap * 8192 + rank * (kHalf * 128), kHalf * 128, wbar);
+        ptx::bulk_load_1d(w2sm + tap * 4096, ap.w2_img + tap * 8192 + rank * (kHalf * 128), kHalf * 128, wbar);
       }
     }
     __syncwarp();
@@ -173,7 +177,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
       __syncwarp();
     } else {
       // ---------------------------------------------------------- leader: both MMA streams, conv_1 two mid rows ahead of conv_2
-      constexpr uint32_t idesc = ptx::idesc_f16_f32(256, 64);
+      constexpr uint32_t idesc = ptx::idesc_f16_f32(256, kN);
       const uint64_t b1 = ptx::smem_desc_sw128(w1sm, 1024, 0);
       const uint64_t b2 = ptx::smem_desc_sw128(w2sm, 1024, 0);
       const uint64_t at0 = ptx::smem_desc_sw128(tring, 1024, 0);
@@ -301,7 +305,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
               const float f0 = epi_apply<EPI_PRELU>(__uint_as_float(v[jj]), p.param, 0.f, 0.f, 0);
               const float f1 = epi_apply<EPI_PRELU>(__uint_as_float(v[jj + 1]), p.param, 0.f, 0.f, 0);
               const __half2 hv = __floats2half2_rn(f0, f1);
-              w[e] = inside ? *reinterpret_cast<const uint32_t*>(&hv) : 0u;
+              w[e] = inside && h * 32 + jj < kN ? *reinterpret_cast<const uint32_t*>(&hv) : 0u;   // accumulator columns >= kN are never written
             }
             pk[h * 4 + q] = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -404,7 +408,7 @@ arsb_pair_kernel(const __grid_constant__ ArsbMaps maps, const ArsbParams ap)
               const float f0 = epi_apply<EPI_SCALE_SKIP>(__uint_as_float(v[jj]), ap.scale, 0.f, __low2float(hs), 0);
               const float f1 = epi_apply<EPI_SCALE_SKIP>(__uint_as_float(v[jj + 1]), ap.scale, 0.f, __high2float(hs), 0);
               const __half2 hv = __floats2half2_rn(f0, f1);
-              w[e] = *reinterpret_cast<const uint32_t*>(&hv);
+              w[e] = h * 32 + jj < kN ? *reinterpret_cast<const uint32_t*>(&hv) : 0u;
             }
             pk[h * 4 + q] = make_uint4(w[0], w[1], w[2], w[3]);
           }
