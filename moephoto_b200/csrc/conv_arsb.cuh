@@ -14,14 +14,17 @@
 //     four more epilogue warps apply q(q(q(acc) * scale) + t): the residual row is still in the t ring, read from
 //     shared memory instead of HBM, and the 126-pixel result row leaves through a staging tile and one TMA store.
 // HBM traffic per pixel-plane: 128 B read (x 130/126 and + 4 halo rows per row segment) + 128 B written.
-// What bounds it is SHARED-MEMORY bandwidth, not HBM and not MMA issue (profiles/r02_arsb_experiments.txt): an M = 256 x N = 64 x
-// K = 16 MMA fetches 4 KB (A) + 1 KB (B half) per SM for 32 cycles of math = 40 cycles at 128 B/clk, 72 of them per row = 360 KB,
-// plus 81 KB of TMA / epilogue traffic = 3 445 cycles per row; measured 3 900.  Moving the output epilogue to global loads and
-// stores, or issuing the two convolutions from two warps, changed nothing (global accesses use the same L1 data path).
+// What bounds it is the SM's SHARED-MEMORY DATA PIPE (one 128-byte wavefront per cycle), not HBM, not MMA issue and not the B
+// exchange between the two SMs (profiles/r02_arsb_experiments.txt): an M = 256 x N = 64 x K = 16 MMA fetches per SM 4 KB of A +
+// 1 KB of its B half and serves 1 KB to its partner = 48 wavefronts for 32 cycles of math; every N = 64 kernel of the engine runs
+// at 49-54 cycles per MMA.  Moving the output epilogue to global loads and stores, issuing the two convolutions from two warps
+// (freely, or taking turns), or giving every SM all the weights (conv_arsb_solo.cuh) changed nothing or made it slower; taking
+// conv_2's A operand out of shared memory (kMidTmem, the default) is worth 2-3 % inside the power-capped frame.
 // MMA issue order (one thread of the leader CTA): conv_1 runs TWO mid rows ahead of conv_2 — C1(y+2), C2(y), C1(y+3),
 // C2(y+1), ... — so the epilogue that turns an accumulator into a mid row overlaps the other convolution's MMAs.
-// Shared memory: 5 x 17 KB t ring + 3 x 16 KB mid ring + 2 x 36 KB weights (this CTA's 32 output channels of both
-// convolutions) + 16 KB staging = 223 KB.  TMEM: 4 + 4 accumulator stages of 64 columns.
+// Shared memory (kMidTmem = false): 5 x 17 KB t ring + 3 x 16 KB mid ring + 2 x 36 KB weights (this CTA's 32 output channels of both
+// convolutions) + 16 KB staging = 223 KB; TMEM: 4 + 4 accumulator stages of 64 columns.  The default form (kMidTmem = true, below)
+// keeps the mid rows in tensor memory instead.
 // Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader) / weight handshake (peer), 2..5 mid epilogue, 6..9 output epilogue.
 #pragma once
 #include "conv_pair.cuh"
