@@ -16,6 +16,10 @@
 //     reference's half model rounds each head to fp16 BEFORE adding them (models.py:38);
 //   * head_stencil_kernel (below) finishes vertically: S = (H_0(Y-1) + H_1(Y)) + H_2(Y+1) per branch, rounds each, adds,
 //     rounds, blends, stores: 2 x 12 + 2 B per output pixel.
+//   * PixelShuffle(3) (a3): the three sub-pixels of an output row belong to different chunk groups (five groups of two chunks),
+//     i.e. to different CTA pairs, so the readers export all nine dot products of every sub-pixel chunk unreduced
+//     (pbuf[n][y][chunk * 9 + tap][W], 324 B per input pixel-plane instead of the 1 152 B of activations) and
+//     head_stencil9_kernel does the whole 3 x 3 gather.
 // Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader) / weight handshake (peer), 2..9 epilogue,
 // 10 head-MMA issuer (leader), 11..14 P readers.  TMEM: 3 accumulator stages x 128 columns + 2 P stages x 32.
 #pragma once
